@@ -1,0 +1,191 @@
+"""
+CPU tests of the oracle (oracle/): the numpy restatement against the reference's
+only value-pinned test, against analytic answers, against the committed golden
+vectors, and against the independent C restatement.
+"""
+import numpy as np
+import pytest
+
+from oracle import c_oracle as co
+from oracle import vegas_ref as R
+
+
+def test_histogram_scatter_like_reference_test_utils():
+    """Restates src/vegasflow/tests/test_utils.py:11-30 (the one pinned test)."""
+    rng = np.random.default_rng(0)
+    size_in = int(rng.integers(5, 100))
+    size_out = int(rng.integers(1, size_in - 3))
+    input_array = rng.random(size_in)
+    indices = rng.integers(0, size_out, size=size_in)
+    result = R.consume_array_into_indices(input_array, indices.reshape(-1, 1), size_out)
+    onehot = R.consume_array_into_indices_onehot(input_array, indices.reshape(-1, 1), size_out)
+    np.testing.assert_allclose(result, onehot, rtol=1e-14)
+    np.testing.assert_almost_equal(np.sum(input_array), np.sum(result))
+    check = np.zeros(size_out)
+    for val, i in zip(input_array, indices):
+        check[i] += val
+    np.testing.assert_allclose(check, result)
+
+
+def test_philox_known_answers():
+    """Random123 kat_vectors for philox4x32-10."""
+    kat = [
+        ([0, 0, 0, 0], [0, 0], [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]),
+        ([0xFFFFFFFF] * 4, [0xFFFFFFFF] * 2, [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]),
+        ([0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344], [0xA4093822, 0x299F31D0],
+         [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]),
+    ]
+    for ctr, key, want in kat:
+        assert list(co.philox4x32_10(ctr, key)) == want
+
+
+def test_uniform_stream_range_and_independence_of_chunking():
+    r = co.uniforms(3, 2, 0, 50000, 5)
+    assert r.min() >= R.TECH_CUT * 0.99 and r.max() < 1 - R.TECH_CUT
+    assert abs(r.mean() - 0.5) < 5e-3
+    a = co.uniforms(3, 2, 1000, 100, 5)
+    np.testing.assert_array_equal(a, r[1000:1100])  # counter-based: offset == slice
+    assert not np.array_equal(co.uniforms(3, 3, 0, 10, 5), r[:10])  # iteration changes stream
+    assert not np.array_equal(co.uniforms(4, 2, 0, 10, 5), r[:10])  # seed changes stream
+
+
+@pytest.mark.parametrize("name,d", [("symgauss", 2), ("symgauss", 4), ("symgauss", 8),
+                                     ("symgauss", 20), ("product", 1), ("product", 3),
+                                     ("product", 8)])
+def test_numpy_vs_c_vs_golden_digest(golden, name, d):
+    key = f"{name}_d{d}"
+    r, grid = golden[key + "_rnds"], golden[key + "_grid"]
+    n = r.shape[0]
+    _, _, hist, det = R.vegas_run_event(r, grid, R.INTEGRANDS[name], n)
+    np.testing.assert_array_equal(det["ind"], golden[key + "_ind"])
+    np.testing.assert_array_equal(det["x"], golden[key + "_x"])
+    np.testing.assert_array_equal(det["w"], golden[key + "_w"])
+    np.testing.assert_allclose(det["wf"], golden[key + "_wf"], rtol=1e-13)
+    x, w, ind, wf = co.digest_from_uniforms(co.MODE_VEGAS, name, r, grid, 1.0 / n)
+    np.testing.assert_array_equal(ind, golden[key + "_ind"])
+    np.testing.assert_array_equal(x, golden[key + "_x"])
+    np.testing.assert_array_equal(w, golden[key + "_w"])
+    np.testing.assert_allclose(wf, golden[key + "_wf"], rtol=1e-12, atol=0)
+    # bins are in range and the extremes of the uniform interval land in bins 49 / 0
+    assert ind.min() >= 0 and ind.max() <= 49
+    assert (ind[0] == 49).all() and (ind[1] == 0).all()
+    np.testing.assert_allclose(co.refine_grid(hist, grid), golden[key + "_newgrid"], rtol=0,
+                               atol=1e-13)
+
+
+def test_limits_and_plain_against_golden(golden):
+    r, grid = golden["limits_rnds"], golden["limits_grid"]
+    xmin, xmax = golden["limits_xmin"], golden["limits_xmax"]
+    n = r.shape[0]
+    x, w, ind, wf = co.digest_from_uniforms(co.MODE_VEGAS, "product", r, grid, 1.0 / n, xmin,
+                                            xmax - xmin)
+    np.testing.assert_array_equal(x, golden["limits_x"])
+    np.testing.assert_array_equal(w, golden["limits_w"])
+    np.testing.assert_array_equal(wf, golden["limits_wf"])
+    assert (x >= xmin).all() and (x <= xmax).all()
+    r = golden["plain_rnds"]
+    _, _, _, wf = co.digest_from_uniforms(co.MODE_PLAIN, "symgauss", r, None, 1.0 / n)
+    np.testing.assert_allclose(wf, golden["plain_wf"], rtol=1e-12)
+
+
+def test_refine_grid_properties():
+    rng = np.random.default_rng(9)
+    grid = R.initial_divisions(3)
+    hist = rng.random((3, 50)) ** 4
+    hist[1, 10:20] = 0.0  # empty bins hit the 1e-30 floor
+    new = R.refine_grid(hist, grid)
+    assert (np.diff(new, axis=1) > 0).all()
+    assert (new[:, 0] == 0).all() and (new[:, -1] == 1).all()
+    np.testing.assert_allclose(co.refine_grid(hist, grid), new, rtol=0, atol=1e-13)
+    # a flat histogram leaves a flat grid unchanged (to rounding)
+    flat = R.refine_grid(np.ones((1, 50)), R.initial_divisions(1))
+    np.testing.assert_allclose(flat, R.initial_divisions(1), atol=1e-12)
+
+
+def test_known_integrals_numpy_oracle():
+    draw = R.uniform_source_numpy(1)
+    res, err, _, _ = R.vegas_integrate(R.symgauss, 4, 100000, 5, draw)
+    assert abs(res - 1.0) < 3 * err
+    res, err, _, _ = R.vegas_integrate(R.product, 8, 100000, 5, draw)
+    assert abs(res - 2.0**-8) < 3 * err
+    xmin, xmax = [-0.5, 0.2], [3.1, 3.9]
+    res, err, _, _ = R.vegas_integrate(R.product, 2, 20000, 5, draw, xmin=xmin, xmax=xmax)
+    want = np.prod(np.array(xmax) ** 2 / 2 - np.array(xmin) ** 2 / 2)
+    assert abs(res - want) < 3 * err
+    res, err, _ = R.plain_integrate(R.product, 3, 100000, 3, draw)
+    assert abs(res - 0.125) < 3 * err
+
+
+def test_c_oracle_integration_on_philox_stream():
+    """Whole VEGAS loop of the C restatement on the engine's own stream."""
+    d, n = 4, 200000
+    grid = R.initial_divisions(d)
+    results = []
+    for it in range(5):
+        s1, s2, hist = co.run_event(co.MODE_VEGAS, "symgauss", d, 0, n, 1.0 / n, 42, it, True, grid)
+        results.append((s1, R.vegas_sigma(s1, s2, n)))
+        grid = co.refine_grid(hist, grid)
+    res, err = R.combine_iterations(results)
+    assert abs(res - 1.0) < 3 * err
+    assert err < 2e-3
+    # chunking / sharding invariance: two half ranges sum to the full range
+    a = co.run_event(co.MODE_VEGAS, "symgauss", d, 0, n // 2, 1.0 / n, 42, 5, True, grid)
+    b = co.run_event(co.MODE_VEGAS, "symgauss", d, n // 2, n - n // 2, 1.0 / n, 42, 5, True, grid)
+    full = co.run_event(co.MODE_VEGAS, "symgauss", d, 0, n, 1.0 / n, 42, 5, True, grid)
+    np.testing.assert_allclose(a[0] + b[0], full[0], rtol=1e-12)
+    np.testing.assert_allclose(a[2] + b[2], full[2], rtol=1e-10)
+
+
+def test_singletop_and_drellyan_known_answers(golden):
+    draw = R.uniform_source_numpy(2)
+    res, err, _, _ = R.vegas_integrate(R.singletop_lo, 3, 100000, 5, draw)
+    assert abs(res - 423.9) < 4 * err + 0.5  # 423.9 +- 0.2 pb
+    x = 1e-8 + np.random.default_rng(0).random((20000, 4)) * (1 - 2e-8)
+    f, g = R.drellyan_lo(x), R.drellyan_closed_form(x)
+    rel = np.abs(f - g) / np.abs(g)
+    assert np.median(rel) < 2e-15 and np.quantile(rel, 0.99) < 1e-13
+    for name, d in (("drellyan_lo", 4), ("singletop_lo", 3)):
+        key = f"{name}_d{d}"
+        n = golden[key + "_rnds"].shape[0]
+        _, _, _, det = R.vegas_run_event(golden[key + "_rnds"], golden[key + "_grid"],
+                                         R.INTEGRANDS[name], n)
+        np.testing.assert_allclose(det["wf"], golden[key + "_wf"], rtol=1e-13)
+        assert np.isfinite(det["wf"]).all() and (det["wf"] > 0).all()
+
+
+def test_plus_setup_matches_survey_table():
+    """SURVEY 9.1 sizes (vflowplus.py:113-139 evaluated in float32)."""
+    want = {(2, 10**4, False): (70, 4900, 2, 9800), (2, 10**4, True): (50, 2500, 2, 5000),
+            (4, 10**6, False): (10, 10000, 100, 10**6),
+            (8, 10**8, False): (3, 6561, 15241, 99996201),
+            (8, 10**8, True): (3, 6561, 7620, 49994820)}
+    for (d, n, ad), (ns, nc, mn, ne) in want.items():
+        st = R.plus_setup(d, n, ad)
+        assert (st["n_strat"], st["n_cubes"], st["min_neval_hcube"], st["n_events"]) == (ns, nc, mn, ne)
+
+
+def test_plus_numpy_vs_c_vs_golden(golden):
+    r, grid, n_ev = golden["plus_rnds"], golden["plus_grid"], golden["plus_n_ev"]
+    n_strat = int(golden["plus_n_strat"])
+    ress, var, hist, det = co.plus_run_event("symgauss", 3, n_strat, n_ev, 1.0 / len(n_ev), 0, 0,
+                                             True, grid, rnds=r, detail=True)
+    np.testing.assert_array_equal(det["ind"], golden["plus_ind"])
+    np.testing.assert_array_equal(det["x"], golden["plus_x"])
+    np.testing.assert_array_equal(det["w"], golden["plus_w"])
+    np.testing.assert_allclose(det["wf"], golden["plus_wf"], rtol=1e-12)
+    np.testing.assert_allclose(ress, golden["plus_ress"], rtol=1e-12)
+    np.testing.assert_allclose(hist, golden["plus_hist"], rtol=1e-11)
+    res, sigma = R.plus_result(golden["plus_ress"], golden["plus_var"], n_ev)
+    assert res == golden["plus_res"] and sigma == golden["plus_sigma"]
+    new_n_ev, total = R.plus_redistribute(golden["plus_var"], int(golden["plus_min_neval"]),
+                                          int(golden["plus_init_calls"]))
+    np.testing.assert_array_equal(new_n_ev, golden["plus_new_n_ev"])
+    assert new_n_ev.min() >= int(golden["plus_min_neval"]) and total == new_n_ev.sum()
+
+
+def test_plus_integrates_to_one():
+    draw = R.uniform_source_numpy(4)
+    res, err, *_ = R.plus_integrate(R.symgauss, 2, 10000, 4, draw)
+    assert abs(res - 1.0) < 3 * err
+    res, err, *_ = R.plus_integrate(R.symgauss, 2, 10000, 4, draw, adaptive=True)
+    assert abs(res - 1.0) < 3 * err

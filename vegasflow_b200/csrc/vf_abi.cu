@@ -1,0 +1,379 @@
+// extern "C" surface declared in include/vegasflow_b200.h.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "vf_aux.cuh"
+#include "vf_event.cuh"
+
+namespace vf {
+
+static thread_local char g_error[512] = "";
+static thread_local int64_t g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("CUDA error %d (%s) at %s", (int)e, cudaGetErrorString(e), what);
+    return VF_ERR_CUDA;
+}
+void count_launch(int n) { g_launches += n; }
+
+int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+            n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+static int make_limits(int n_dim, const double* xmin, const double* xdelta, Limits* lim) {
+    memset(lim, 0, sizeof(*lim));
+    if ((xmin == nullptr) != (xdelta == nullptr)) {
+        set_error("xmin and xdelta must both be given or both be NULL");
+        return VF_ERR_INVALID;
+    }
+    if (!xmin) return VF_OK;
+    if (n_dim > kMaxDim) {
+        set_error("integration limits support n_dim <= %d", kMaxDim);
+        return VF_ERR_UNSUPPORTED;
+    }
+    lim->has = 1;
+    double jac = xdelta[0];  // tf.reduce_prod(xdelta), monte_carlo.py:171, left to right
+    for (int j = 1; j < n_dim; ++j) jac = jac * xdelta[j];
+    lim->xdeltajac = jac;
+    for (int j = 0; j < n_dim; ++j) {
+        lim->xmin[j] = xmin[j];
+        lim->xdelta[j] = xdelta[j];
+    }
+    return VF_OK;
+}
+
+// Host constants of the built-in integrands.
+static void fill_consts(int integrand, int n_dim, IntegrandConsts* ic) {
+    memset(ic, 0, sizeof(*ic));
+    if (integrand == VF_INTEGRAND_SYMGAUSS) {
+        // examples/simgauss_tf.py:26-31
+        const double a = 0.1;
+        const double n100 = 100.0 * n_dim;
+        ic->p[0] = std::pow(1.0 / a / std::sqrt(M_PI), (double)n_dim);
+        ic->p[1] = (n100 + 1) * n100 / 2.0;
+    }
+}
+
+static size_t workspace_need(int n_dim) {
+    return ((size_t)kMaxBlocks * partial_stride(n_dim) + 2) * sizeof(double);
+}
+
+static int check_common(int n_dim, int64_t n) {
+    if (n_dim < 1) {
+        set_error("n_dim must be >= 1 (got %d)", n_dim);
+        return VF_ERR_INVALID;
+    }
+    if (n < 0) {
+        set_error("negative event count");
+        return VF_ERR_INVALID;
+    }
+    return VF_OK;
+}
+
+template <class F>
+static int dispatch_integrand(int integrand, F&& f) {
+    switch (integrand) {
+        case VF_INTEGRAND_SYMGAUSS: return f(SymGauss{});
+        case VF_INTEGRAND_PRODUCT: return f(Product{});
+        case VF_INTEGRAND_DRELLYAN_LO: return f(DrellYanLO{});
+        case VF_INTEGRAND_SINGLETOP_LO: return f(SingleTopLO{});
+        default:
+            set_error("unknown integrand id %d", integrand);
+            return VF_ERR_INVALID;
+    }
+}
+
+}  // namespace vf
+
+using namespace vf;
+
+extern "C" {
+
+int vf_version(void) { return VF_ABI_VERSION; }
+const char* vf_last_error(void) { return g_error; }
+
+int vf_integrand_id(const char* name) {
+    if (!name) return VF_ERR_INVALID;
+    if (!strcmp(name, "symgauss")) return VF_INTEGRAND_SYMGAUSS;
+    if (!strcmp(name, "product")) return VF_INTEGRAND_PRODUCT;
+    if (!strcmp(name, "drellyan_lo")) return VF_INTEGRAND_DRELLYAN_LO;
+    if (!strcmp(name, "singletop_lo")) return VF_INTEGRAND_SINGLETOP_LO;
+    set_error("unknown integrand '%s'", name);
+    return VF_ERR_INVALID;
+}
+
+int vf_supported(int integrand, int n_dim) {
+    switch (integrand) {
+        case VF_INTEGRAND_SYMGAUSS: return supported_dim<SymGauss>(n_dim);
+        case VF_INTEGRAND_PRODUCT: return supported_dim<Product>(n_dim);
+        case VF_INTEGRAND_DRELLYAN_LO: return supported_dim<DrellYanLO>(n_dim);
+        case VF_INTEGRAND_SINGLETOP_LO: return supported_dim<SingleTopLO>(n_dim);
+        default: return 0;
+    }
+}
+
+double vf_flops_per_event(int mode, int integrand, int n_dim, int plus) {
+    // add/sub/mul/div = 1, each transcendental = 1.
+    const double d = n_dim;
+    double base = mode == VF_MODE_VEGAS ? 12.0 * d + 5.0 : 3.0 * d + 5.0;
+    if (plus) base += d + 1.0;
+    switch (integrand) {
+        case VF_INTEGRAND_SYMGAUSS: return base + 4.0 * d + 4.0;
+        case VF_INTEGRAND_PRODUCT: return base + (d - 1.0);
+        case VF_INTEGRAND_DRELLYAN_LO: return base + 560.0;   // hand count, DESIGN.md
+        case VF_INTEGRAND_SINGLETOP_LO: return base + 900.0;  // hand count, DESIGN.md
+        default: return base;
+    }
+}
+
+size_t vf_workspace_bytes(int n_dim) { return n_dim < 1 ? 0 : workspace_need(n_dim); }
+
+int vf_run_event(int mode, int integrand, int n_dim, uint64_t ev_begin, int64_t n_events,
+                 double xjac, uint64_t seed, uint32_t iteration, int train,
+                 const double* divisions, const double* xmin, const double* xdelta,
+                 double* out_sums, double* out_hist, int accumulate, void* workspace,
+                 size_t workspace_bytes, void* stream) {
+    int rc = check_common(n_dim, n_events);
+    if (rc) return rc;
+    if (mode != VF_MODE_PLAIN && mode != VF_MODE_VEGAS) {
+        set_error("unknown mode %d", mode);
+        return VF_ERR_INVALID;
+    }
+    if (mode == VF_MODE_VEGAS && !divisions) {
+        set_error("VEGAS mode needs a divisions grid");
+        return VF_ERR_INVALID;
+    }
+    const bool with_hist = mode == VF_MODE_VEGAS && train;
+    if (!out_sums || (with_hist && !out_hist) || !workspace) {
+        set_error("null output/workspace pointer");
+        return VF_ERR_INVALID;
+    }
+    if (workspace_bytes < workspace_need(n_dim)) {
+        set_error("workspace too small: %zu < %zu", workspace_bytes, workspace_need(n_dim));
+        return VF_ERR_WORKSPACE;
+    }
+    EventLaunch L;
+    L.mode = mode;
+    L.n_dim = n_dim;
+    L.stream = (cudaStream_t)stream;
+    int nblocks = 0;
+    L.nblocks_out = &nblocks;
+    rc = make_limits(n_dim, xmin, xdelta, &L.k.lim);
+    if (rc) return rc;
+    fill_consts(integrand, n_dim, &L.k.ic);
+    L.k.divisions = divisions;
+    L.k.partials = (double*)workspace;
+    L.k.ev_begin = ev_begin;
+    L.k.ev_end = ev_begin + (uint64_t)n_events;
+    L.k.xjac = xjac;
+    L.k.seed_lo = (uint32_t)seed;
+    L.k.seed_hi = (uint32_t)(seed >> 32);
+    L.k.iteration = iteration;
+    L.k.train = train;
+    rc = dispatch_integrand(integrand, [&](auto tag) { return launch_event<decltype(tag)>(L); });
+    if (rc) return rc;
+    return launch_finalize((const double*)workspace, nblocks, n_dim, with_hist, out_sums, out_hist,
+                           accumulate, L.stream);
+}
+
+int vf_refine_grid(int n_dim, const double* hist, double* divisions, void* stream) {
+    if (n_dim < 1 || !hist || !divisions) {
+        set_error("vf_refine_grid: bad arguments");
+        return VF_ERR_INVALID;
+    }
+    return launch_refine(n_dim, hist, divisions, (cudaStream_t)stream);
+}
+
+int vf_iteration_epilogue(int n_dim, int64_t n_events, int train, const double* sums,
+                          const double* hist, double* divisions, double* result, void* stream) {
+    if (n_dim < 1 || !sums || !result || (train && (!hist || !divisions))) {
+        set_error("vf_iteration_epilogue: bad arguments");
+        return VF_ERR_INVALID;
+    }
+    return launch_epilogue(n_dim, n_events, train, sums, hist, divisions, result,
+                           (cudaStream_t)stream);
+}
+
+int vf_digest_from_uniforms(int mode, int integrand, int n_dim, int64_t n, const double* rnds,
+                            const double* divisions, double xjac, const double* xmin,
+                            const double* xdelta, double* x, double* w, int32_t* ind, double* wf,
+                            void* stream) {
+    int rc = check_common(n_dim, n);
+    if (rc) return rc;
+    if (n == 0) return VF_OK;
+    if (!rnds || (mode == VF_MODE_VEGAS && !divisions)) {
+        set_error("vf_digest_from_uniforms: null input");
+        return VF_ERR_INVALID;
+    }
+    DigestLaunch L;
+    L.mode = mode;
+    L.n_dim = n_dim;
+    L.stream = (cudaStream_t)stream;
+    rc = make_limits(n_dim, xmin, xdelta, &L.k.lim);
+    if (rc) return rc;
+    fill_consts(integrand, n_dim, &L.k.ic);
+    L.k.rnds = rnds;
+    L.k.divisions = divisions;
+    L.k.x = x;
+    L.k.w = w;
+    L.k.ind = ind;
+    L.k.wf = wf;
+    L.k.n = n;
+    L.k.xjac = xjac;
+    return dispatch_integrand(integrand,
+                              [&](auto tag) { return launch_digest<decltype(tag)>(L); });
+}
+
+int vf_uniforms(int n_dim, uint64_t ev_begin, int64_t n, uint64_t seed, uint32_t iteration,
+                double* rnds, void* stream) {
+    int rc = check_common(n_dim, n);
+    if (rc) return rc;
+    return launch_uniforms(n_dim, ev_begin, n, seed, iteration, rnds, (cudaStream_t)stream);
+}
+
+int vf_sample(int mode, int n_dim, uint64_t ev_begin, int64_t n, double xjac, uint64_t seed,
+              uint32_t iteration, const double* divisions, const double* xmin,
+              const double* xdelta, double* x, double* w, int32_t* ind, void* stream) {
+    int rc = check_common(n_dim, n);
+    if (rc) return rc;
+    if (n_dim > kMaxDim) {
+        set_error("vf_sample supports n_dim <= %d", kMaxDim);
+        return VF_ERR_UNSUPPORTED;
+    }
+    if (!x || !w || (mode == VF_MODE_VEGAS && !divisions)) {
+        set_error("vf_sample: null pointer");
+        return VF_ERR_INVALID;
+    }
+    Limits lim;
+    rc = make_limits(n_dim, xmin, xdelta, &lim);
+    if (rc) return rc;
+    return launch_sample(mode, n_dim, ev_begin, n, xjac, seed, iteration, divisions, lim, x, w, ind,
+                         (cudaStream_t)stream);
+}
+
+int vf_accumulate(int n_dim, int64_t n, const double* w, const double* f, const int32_t* ind,
+                  int train, double* out_sums, double* out_hist, int accumulate, void* workspace,
+                  size_t workspace_bytes, void* stream) {
+    int rc = check_common(n_dim, n);
+    if (rc) return rc;
+    if (n_dim > kMaxDim) {
+        set_error("vf_accumulate supports n_dim <= %d", kMaxDim);
+        return VF_ERR_UNSUPPORTED;
+    }
+    const bool with_hist = train && ind && out_hist;
+    if (!w || !f || !out_sums || !workspace) {
+        set_error("vf_accumulate: null pointer");
+        return VF_ERR_INVALID;
+    }
+    if (workspace_bytes < workspace_need(n_dim)) {
+        set_error("workspace too small");
+        return VF_ERR_WORKSPACE;
+    }
+    int nblocks = 0;
+    rc = launch_accumulate(n_dim, n, w, f, ind, with_hist, (double*)workspace, &nblocks,
+                           (cudaStream_t)stream);
+    if (rc) return rc;
+    return launch_finalize((const double*)workspace, nblocks, n_dim, with_hist, out_sums, out_hist,
+                           accumulate, (cudaStream_t)stream);
+}
+
+int vfp_run_event(int integrand, int n_dim, int n_strat, int64_t n_cubes, int64_t n_events,
+                  const int32_t* n_ev, const int64_t* ev_offset, double xjac, uint64_t seed,
+                  uint32_t iteration, int train, const double* divisions, const double* xmin,
+                  const double* xdelta, double* ress, double* ress2, double* out_hist,
+                  int accumulate, void* workspace, size_t workspace_bytes, const double* rnds,
+                  double* x, double* w, int32_t* ind, double* wf, void* stream) {
+    int rc = check_common(n_dim, n_events);
+    if (rc) return rc;
+    if (!n_ev || !ev_offset || !divisions || !ress || !ress2 || !workspace ||
+        (train && !out_hist) || n_strat < 1 || n_cubes < 1) {
+        set_error("vfp_run_event: bad arguments");
+        return VF_ERR_INVALID;
+    }
+    if (workspace_bytes < workspace_need(n_dim)) {
+        set_error("workspace too small");
+        return VF_ERR_WORKSPACE;
+    }
+    PlusLaunch L;
+    L.n_dim = n_dim;
+    L.stream = (cudaStream_t)stream;
+    int nblocks = 0;
+    L.nblocks_out = &nblocks;
+    rc = make_limits(n_dim, xmin, xdelta, &L.k.lim);
+    if (rc) return rc;
+    fill_consts(integrand, n_dim, &L.k.ic);
+    L.k.divisions = divisions;
+    L.k.partials = (double*)workspace;
+    L.k.n_ev = n_ev;
+    L.k.ev_offset = ev_offset;
+    L.k.ress = ress;
+    L.k.ress2 = ress2;
+    L.k.rnds = rnds;
+    L.k.x = x;
+    L.k.w = w;
+    L.k.ind = ind;
+    L.k.wf = wf;
+    L.k.n_cubes = n_cubes;
+    L.k.n_events = n_events;
+    L.k.n_strat = n_strat;
+    L.k.xjac = xjac;
+    L.k.seed_lo = (uint32_t)seed;
+    L.k.seed_hi = (uint32_t)(seed >> 32);
+    L.k.iteration = iteration;
+    L.k.train = train;
+    rc = dispatch_integrand(integrand, [&](auto tag) { return launch_plus<decltype(tag)>(L); });
+    if (rc) return rc;
+    if (!train) return VF_OK;
+    // histogram only: the scalar block writes into a scratch pair past the partial records
+    double* scratch_sums = (double*)workspace + (size_t)kMaxBlocks * partial_stride(n_dim);
+    return launch_finalize((const double*)workspace, nblocks, n_dim, true, scratch_sums, out_hist,
+                           accumulate, L.stream);
+}
+
+int vfp_iteration_epilogue(int64_t n_cubes, const double* ress, const double* ress2, int adaptive,
+                           int min_neval_hcube, int64_t init_calls, int32_t* n_ev,
+                           int64_t* ev_offset, double* arr_var, double* result,
+                           int64_t* n_events_out, void* stream) {
+    if (n_cubes < 1 || !ress || !ress2 || !n_ev || !arr_var || !result ||
+        (adaptive && (!ev_offset || !n_events_out))) {
+        set_error("vfp_iteration_epilogue: bad arguments");
+        return VF_ERR_INVALID;
+    }
+    return launch_plus_epilogue(n_cubes, ress, ress2, adaptive, min_neval_hcube, init_calls, n_ev,
+                                ev_offset, arr_var, result, n_events_out, (cudaStream_t)stream);
+}
+
+int vf_fp64_peak_probe(int iters, double* tflops) {
+    if (iters < 1 || !tflops) {
+        set_error("vf_fp64_peak_probe: bad arguments");
+        return VF_ERR_INVALID;
+    }
+    return run_fp64_probe(iters, tflops);
+}
+
+int vf_sm_count(void) { return sm_count(); }
+
+int64_t vf_launch_count(int reset) {
+    const int64_t v = g_launches;
+    if (reset) g_launches = 0;
+    return v;
+}
+
+}  // extern "C"

@@ -1,0 +1,113 @@
+// Shared device/host definitions for the vegasflow_b200 kernels (sm_100a).
+// Reference citations are file:line relative to /root/reference.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/vegasflow_b200.h"
+
+namespace vf {
+
+constexpr int kBins = VF_BINS_MAX;        // configflow.py:13
+constexpr int kEdges = VF_BINS_MAX + 1;   // vflow.py:239
+constexpr double kFBins = 50.0;           // vflow.py:30
+constexpr double kTechCut = 1e-8;         // configflow.py:16
+constexpr double kAlpha = 1.5;            // configflow.py:14
+constexpr double kBeta = 0.75;            // configflow.py:15
+constexpr int kMaxDim = 32;               // limits arrays passed by value
+constexpr double kTwo52 = 4503599627370496.0;
+
+// ---- host-side error plumbing (vf_abi.cu) ---------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+void count_launch(int n = 1);
+int sm_count();
+
+#define VF_CUDA_CHECK(expr)                                   \
+    do {                                                      \
+        cudaError_t _e = (expr);                              \
+        if (_e != cudaSuccess) return vf::cuda_fail(_e, #expr); \
+    } while (0)
+
+// Integration limits, passed by value into kernel parameter space
+// (monte_carlo.py:159-175).  has == 0 -> unit hypercube.
+struct Limits {
+    int has;
+    double xdeltajac;  // prod_j xdelta[j], left to right (monte_carlo.py:171)
+    double xmin[kMaxDim];
+    double xdelta[kMaxDim];
+};
+
+// Constants of the built-in integrands, filled on the host.
+struct IntegrandConsts {
+    double p[4];
+};
+
+// ---- Philox4x32-10 ---------------------------------------------------------
+// The engine's own counter-based stream (the reference delegates to
+// tf.random.uniform, monte_carlo.py:264-266).  Identical to
+// oracle/vegas_oracle.c::vfo_philox4x32_10.
+constexpr uint32_t kPhiloxM0 = 0xD2511F53u;
+constexpr uint32_t kPhiloxM1 = 0xCD9E8D57u;
+constexpr uint32_t kPhiloxW0 = 0x9E3779B9u;
+constexpr uint32_t kPhiloxW1 = 0xBB67AE85u;
+
+__host__ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2,
+                                                        uint32_t c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)kPhiloxM0 * c0;
+        const uint64_t p1 = (uint64_t)kPhiloxM1 * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1;
+        c3 = (uint32_t)p0;
+        c0 = n0;
+        c2 = n2;
+        k0 += kPhiloxW0;
+        k1 += kPhiloxW1;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
+// Two words -> uniform double in [TECH_CUT, 1-TECH_CUT): 52-bit mantissa fill
+// m in [1,2), then r = fma(m, S, T-S) = T + (m-1)*S with one rounding.
+__device__ __forceinline__ double u52_to_uniform(uint32_t hi, uint32_t lo) {
+    const double m = __hiloint2double((int)(0x3FF00000u | (hi & 0xFFFFFu)), (int)lo);
+    constexpr double S = 1.0 - 2.0 * kTechCut;
+    constexpr double C = kTechCut - S;
+    return fma(m, S, C);
+}
+
+// ---- VEGAS map, one dimension ----------------------------------------------
+// vflow.py:117 (xn = 50*(1-r)), :67 (ind = trunc), :70-76 (x), :78 (Delta*50).
+// `tbl` points at the (x_ini, Delta) pairs of this dimension in shared memory,
+// replicated TC times: tbl[bin*TC + slot]; Delta = x_fin - x_ini (:73) is
+// evaluated once per bin when the table is staged -- same IEEE operation on
+// the same operands as the per-event form.
+template <int TC>
+__device__ __forceinline__ void vegas_map_dim(double xn, const double2* __restrict__ tbl, int slot,
+                                              double& x, double& wfac, int& bin) {
+    // floor via round-down add of 2^52: t = floor(xn) + 2^52 exactly for 0 <= xn < 2^31;
+    // the integer sits in the low mantissa word (== C truncation, vflow.py:67).
+    const double t = __dadd_rd(xn, kTwo52);
+    bin = __double2loint(t);
+    const double fl = __dsub_rn(t, kTwo52);   // tf.math.floor(xn), vflow.py:75
+    const double aux = __dsub_rn(xn, fl);     // :75
+    const double2 e = tbl[bin * TC + slot];
+    x = __dadd_rn(e.x, __dmul_rn(e.y, aux));  // :76, mul then add
+    wfac = __dmul_rn(e.y, kFBins);            // :78
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Layout of one block's partial results in the workspace.
+__host__ __device__ inline size_t partial_stride(int n_dim) { return 2 + (size_t)n_dim * kBins; }
+
+constexpr int kMaxBlocks = 2048;  // upper bound on event-kernel grid size
+
+}  // namespace vf

@@ -1,0 +1,504 @@
+// Fused VEGAS event kernels (sm_100a): Philox -> grid map -> integrand ->
+// reductions + shared-memory histograms, one launch per chunk of events.
+// Reference citations are file:line relative to /root/reference.
+#pragma once
+#include "vf_common.cuh"
+#include "vf_integrands.cuh"
+
+namespace vf {
+
+// Per-dimension-count launch configuration.  Shared memory per block:
+//   table  NDIM*50*TC*16 B  (x_ini, Delta) pairs, TC lane-interleaved copies
+//   hist   NDIM*50*HC*8  B  histogram, HC lane-interleaved copies
+// Interleaving by (lane % copies) makes the LDS.128 table reads (8 lanes per
+// phase) and the 64-bit histogram updates (16 lanes per phase) bank-conflict
+// free for any bin pattern, and leaves same-address collisions only between
+// lanes l and l+HC (probability 1/50 per pair).
+template <int NDIM>
+struct Cfg {
+    static constexpr int kThreads = 512;
+    static constexpr int kMinBlocks = (NDIM <= 8) ? 2 : 1;
+    static constexpr int TC = (NDIM <= 8) ? 8 : 4;
+    static constexpr int HC = (NDIM <= 8) ? 16 : ((NDIM <= 12) ? 8 : 4);
+    static constexpr int kTblEntries = NDIM * kBins * TC;
+    static constexpr int kHistEntries = NDIM * kBins * HC;
+    static constexpr size_t kSmemBytes = (size_t)kTblEntries * 16 + (size_t)kHistEntries * 8;
+};
+// Resident blocks per SM the kernel is compiled for (register budget 64 vs 128).
+template <class I, int NDIM>
+constexpr int min_blocks() {
+    return (I::kHeavy || Cfg<NDIM>::kMinBlocks == 1) ? 1 : 2;
+}
+
+struct EventKernelArgs {
+    const double* divisions;  // [NDIM][51]
+    double* partials;         // [gridDim.x][2 + NDIM*50]
+    uint64_t ev_begin, ev_end;
+    double xjac;
+    uint32_t seed_lo, seed_hi, iteration;
+    int train;
+    Limits lim;
+    IntegrandConsts ic;
+};
+
+// Stage (x_ini, Delta) pairs and zero the histogram copies.
+template <int NDIM>
+__device__ __forceinline__ void stage_grid(const double* __restrict__ divisions, double2* tbl,
+                                           double* hist, bool zero_hist) {
+    using C = Cfg<NDIM>;
+    for (int i = threadIdx.x; i < C::kTblEntries; i += blockDim.x) {
+        const int jb = i / C::TC;
+        const int j = jb / kBins, b = jb - j * kBins;
+        const double x_ini = divisions[j * kEdges + b];      // vflow.py:70
+        const double x_fin = divisions[j * kEdges + b + 1];  // vflow.py:71
+        tbl[i] = make_double2(x_ini, __dsub_rn(x_fin, x_ini));  // vflow.py:73
+    }
+    if (zero_hist)
+        for (int i = threadIdx.x; i < C::kHistEntries; i += blockDim.x) hist[i] = 0.0;
+}
+
+// monte_carlo.py:270-274: w *= xjac; x = xmin + x*xdelta; w *= prod(xdelta)
+template <int NDIM>
+__device__ __forceinline__ double apply_jacobians(double w, double (&x)[NDIM], double xjac,
+                                                  const Limits& lim) {
+    w = __dmul_rn(w, xjac);
+    if (lim.has) {
+#pragma unroll
+        for (int j = 0; j < NDIM; ++j)
+            x[j] = __dadd_rn(lim.xmin[j], __dmul_rn(x[j], lim.xdelta[j]));
+        w = __dmul_rn(w, lim.xdeltajac);
+    }
+    return w;
+}
+
+// Block-level tail shared by the event kernels: reduce the two scalars and the
+// histogram copies in a fixed order and write this block's partial record.
+template <int NDIM>
+__device__ __forceinline__ void write_partials(double sum, double sum2, const double* hist,
+                                               bool with_hist, double* partials) {
+    using C = Cfg<NDIM>;
+    __shared__ double red[2][C::kThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    sum = warp_sum(sum);
+    sum2 = warp_sum(sum2);
+    if (lane == 0) {
+        red[0][warp] = sum;
+        red[1][warp] = sum2;
+    }
+    __syncthreads();  // also orders the shared-memory histogram updates
+    double* out = partials + (size_t)blockIdx.x * partial_stride(NDIM);
+    if (threadIdx.x < 2) {
+        double t = 0.0;
+        for (int w = 0; w < C::kThreads / 32; ++w) t += red[threadIdx.x][w];
+        out[threadIdx.x] = t;
+    }
+    for (int i = threadIdx.x; i < NDIM * kBins; i += blockDim.x) {
+        double t = 0.0;
+        if (with_hist) {
+#pragma unroll
+            for (int c = 0; c < C::HC; ++c) t += hist[i * C::HC + c];
+        }
+        out[2 + i] = t;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K1: fused event kernel (VegasFlow._run_event, vflow.py:389-430; PlainFlow
+// plain.py:18-35).  Thread t evaluates global events ev_begin + t, + stride...
+// ---------------------------------------------------------------------------
+template <class I, int NDIM, int MODE>
+__global__ void __launch_bounds__(Cfg<NDIM>::kThreads, min_blocks<I, NDIM>())
+event_kernel(const __grid_constant__ EventKernelArgs a) {
+    using C = Cfg<NDIM>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2* tbl = reinterpret_cast<double2*>(smem_raw);
+    double* hist = reinterpret_cast<double*>(smem_raw + (size_t)C::kTblEntries * 16);
+    const bool do_hist = (MODE == VF_MODE_VEGAS) && a.train;
+    if (MODE == VF_MODE_VEGAS) {
+        stage_grid<NDIM>(a.divisions, tbl, hist, do_hist);
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31;
+    const int tslot = lane % C::TC, hslot = lane % C::HC;
+    double sum = 0.0, sum2 = 0.0;
+    const uint64_t stride = (uint64_t)gridDim.x * C::kThreads;
+    for (uint64_t n = a.ev_begin + (uint64_t)blockIdx.x * C::kThreads + threadIdx.x; n < a.ev_end;
+         n += stride) {
+        double x[NDIM];
+        int bin[NDIM];
+        double w = 1.0;
+#pragma unroll
+        for (int p = 0; p < (NDIM + 1) / 2; ++p) {
+            const uint4 o = philox4x32_10((uint32_t)n, (uint32_t)(n >> 32), (uint32_t)p,
+                                          a.iteration, a.seed_lo, a.seed_hi);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int j = 2 * p + h;
+                if (j < NDIM) {
+                    const double r = h == 0 ? u52_to_uniform(o.x, o.y) : u52_to_uniform(o.z, o.w);
+                    if (MODE == VF_MODE_VEGAS) {
+                        const double xn = __dmul_rn(kFBins, __dsub_rn(1.0, r));  // vflow.py:117
+                        double wfac;
+                        vegas_map_dim<C::TC>(xn, tbl + j * kBins * C::TC, tslot, x[j], wfac,
+                                             bin[j]);
+                        w = (j == 0) ? wfac : __dmul_rn(w, wfac);  // reduce_prod, vflow.py:78
+                    } else {
+                        x[j] = r;  // monte_carlo.py:290-298
+                    }
+                }
+            }
+        }
+        w = apply_jacobians<NDIM>(w, x, a.xjac, a.lim);
+        const double f = I::template eval<NDIM>(x, a.ic);  // vflow.py:412
+        const double tmp = __dmul_rn(w, f);                // vflow.py:416
+        const double tmp2 = __dmul_rn(tmp, tmp);           // vflow.py:417
+        sum += tmp;                                        // vflow.py:420
+        sum2 += tmp2;                                      // vflow.py:421
+        if (do_hist) {                                     // vflow.py:370-387, utils.py:40-43
+#pragma unroll
+            for (int j = 0; j < NDIM; ++j)
+                atomicAdd(&hist[(j * kBins + bin[j]) * C::HC + hslot], tmp2);
+        }
+    }
+    write_partials<NDIM>(sum, sum2, hist, do_hist, a.partials);
+}
+
+// ---------------------------------------------------------------------------
+// K4: parity kernel -- same device code, external uniforms, per-event outputs.
+// ---------------------------------------------------------------------------
+struct DigestKernelArgs {
+    const double* rnds;       // [n][NDIM]
+    const double* divisions;
+    double* x;
+    double* w;
+    int32_t* ind;
+    double* wf;
+    int64_t n;
+    double xjac;
+    Limits lim;
+    IntegrandConsts ic;
+};
+
+template <class I, int NDIM, int MODE>
+__global__ void __launch_bounds__(Cfg<NDIM>::kThreads, min_blocks<I, NDIM>())
+digest_kernel(const __grid_constant__ DigestKernelArgs a) {
+    using C = Cfg<NDIM>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2* tbl = reinterpret_cast<double2*>(smem_raw);
+    if (MODE == VF_MODE_VEGAS) {
+        stage_grid<NDIM>(a.divisions, tbl, nullptr, false);
+        __syncthreads();
+    }
+    const int tslot = (threadIdx.x & 31) % C::TC;
+    for (int64_t n = (int64_t)blockIdx.x * C::kThreads + threadIdx.x; n < a.n;
+         n += (int64_t)gridDim.x * C::kThreads) {
+        double x[NDIM];
+        int bin[NDIM];
+        double w = 1.0;
+#pragma unroll
+        for (int j = 0; j < NDIM; ++j) {
+            const double r = a.rnds[n * NDIM + j];
+            if (MODE == VF_MODE_VEGAS) {
+                const double xn = __dmul_rn(kFBins, __dsub_rn(1.0, r));
+                double wfac;
+                vegas_map_dim<C::TC>(xn, tbl + j * kBins * C::TC, tslot, x[j], wfac, bin[j]);
+                w = (j == 0) ? wfac : __dmul_rn(w, wfac);
+            } else {
+                x[j] = r;
+                bin[j] = 0;
+            }
+        }
+        w = apply_jacobians<NDIM>(w, x, a.xjac, a.lim);
+        const double f = I::template eval<NDIM>(x, a.ic);
+        const double tmp = __dmul_rn(w, f);
+#pragma unroll
+        for (int j = 0; j < NDIM; ++j) {
+            if (a.x) a.x[n * NDIM + j] = x[j];
+            if (a.ind) a.ind[n * NDIM + j] = bin[j];
+        }
+        if (a.w) a.w[n] = w;
+        if (a.wf) a.wf[n] = tmp;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// VEGAS+ fused event kernel (generate_samples_in_hypercubes vflowplus.py:46-80,
+// VegasFlowPlus._run_event vflowplus.py:187-220).  Events are ordered by cube;
+// each block owns a contiguous slice of the event range, its threads stride
+// through it, and a thread re-locates its cube only when it walks past the end
+// of the current one.  Per-cube sums go to global memory with fp64 RED.
+// ---------------------------------------------------------------------------
+struct PlusKernelArgs {
+    const double* divisions;
+    double* partials;
+    const int32_t* n_ev;       // [n_cubes]
+    const int64_t* ev_offset;  // [n_cubes+1]
+    double* ress;              // [n_cubes]
+    double* ress2;             // [n_cubes]
+    const double* rnds;        // external uniforms (EXT) or null
+    double* x;
+    double* w;
+    int32_t* ind;
+    double* wf;
+    int64_t n_cubes, n_events;
+    int n_strat;
+    double xjac;
+    uint32_t seed_lo, seed_hi, iteration;
+    int train;
+    Limits lim;
+    IntegrandConsts ic;
+};
+
+template <class I, int NDIM, bool EXT>
+__global__ void __launch_bounds__(Cfg<NDIM>::kThreads, min_blocks<I, NDIM>())
+plus_event_kernel(const __grid_constant__ PlusKernelArgs a) {
+    using C = Cfg<NDIM>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double2* tbl = reinterpret_cast<double2*>(smem_raw);
+    double* hist = reinterpret_cast<double*>(smem_raw + (size_t)C::kTblEntries * 16);
+    const bool do_hist = a.train != 0;
+    stage_grid<NDIM>(a.divisions, tbl, hist, do_hist);
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int tslot = lane % C::TC, hslot = lane % C::HC;
+    const int64_t per_block = (a.n_events + gridDim.x - 1) / gridDim.x;
+    const int64_t begin = (int64_t)blockIdx.x * per_block;
+    const int64_t end = min(begin + per_block, a.n_events);
+    const double fstrat = (double)a.n_strat;
+
+    int64_t cube = -1, hi = 0;
+    double s1 = 0.0, s2 = 0.0, fn = 1.0;
+    double coords[NDIM];
+    double hsum2 = 0.0;  // unused scalar partials (kept zero)
+    for (int64_t e = begin + threadIdx.x; e < end; e += C::kThreads) {
+        if (e >= hi) {
+            if (cube >= 0) {
+                atomicAdd(&a.ress[cube], s1);   // segment_sum, vflowplus.py:213
+                atomicAdd(&a.ress2[cube], s2);  // vflowplus.py:214
+                s1 = 0.0;
+                s2 = 0.0;
+            }
+            // largest c with ev_offset[c] <= e  (tf.repeat(arange, n_ev), vflowplus.py:67)
+            int64_t lo_c = cube < 0 ? 0 : cube + 1, hi_c = a.n_cubes;  // search in (lo_c, hi_c]
+            while (lo_c < hi_c - 1) {
+                const int64_t mid = (lo_c + hi_c) >> 1;
+                if (a.ev_offset[mid] <= e) lo_c = mid; else hi_c = mid;
+            }
+            cube = lo_c;
+            hi = a.ev_offset[cube + 1];
+            fn = (double)a.n_ev[cube];  // vflowplus.py:69
+            int64_t rem = cube;         // itertools.product order, vflowplus.py:126-128
+#pragma unroll
+            for (int j = NDIM - 1; j >= 0; --j) {
+                const int64_t q = rem / a.n_strat;
+                coords[j] = (double)(rem - q * a.n_strat);
+                rem = q;
+            }
+        }
+        double x[NDIM];
+        int bin[NDIM];
+        double w = 1.0;
+#pragma unroll
+        for (int p = 0; p < (NDIM + 1) / 2; ++p) {
+            uint4 o;
+            if (!EXT)
+                o = philox4x32_10((uint32_t)e, (uint32_t)((uint64_t)e >> 32), (uint32_t)p,
+                                  a.iteration, a.seed_lo, a.seed_hi);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int j = 2 * p + h;
+                if (j < NDIM) {
+                    double r;
+                    if (EXT) r = a.rnds[e * NDIM + j];
+                    else r = h == 0 ? u52_to_uniform(o.x, o.y) : u52_to_uniform(o.z, o.w);
+                    // vflowplus.py:72: (points + rnds) * FBINS / n_strat
+                    const double xn =
+                        __ddiv_rn(__dmul_rn(__dadd_rn(coords[j], r), kFBins), fstrat);
+                    double wfac;
+                    vegas_map_dim<C::TC>(xn, tbl + j * kBins * C::TC, tslot, x[j], wfac, bin[j]);
+                    w = (j == 0) ? wfac : __dmul_rn(w, wfac);
+                }
+            }
+        }
+        w = __ddiv_rn(w, fn);  // vflowplus.py:77
+        w = apply_jacobians<NDIM>(w, x, a.xjac, a.lim);
+        const double f = I::template eval<NDIM>(x, a.ic);
+        const double tmp = __dmul_rn(w, f);       // vflowplus.py:209
+        const double tmp2 = __dmul_rn(tmp, tmp);  // vflowplus.py:210
+        s1 += tmp;
+        s2 += tmp2;
+        if (do_hist) {
+#pragma unroll
+            for (int j = 0; j < NDIM; ++j)
+                atomicAdd(&hist[(j * kBins + bin[j]) * C::HC + hslot], tmp2);
+        }
+        if (EXT) {
+#pragma unroll
+            for (int j = 0; j < NDIM; ++j) {
+                if (a.x) a.x[e * NDIM + j] = x[j];
+                if (a.ind) a.ind[e * NDIM + j] = bin[j];
+            }
+            if (a.w) a.w[e] = w;
+            if (a.wf) a.wf[e] = tmp;
+        }
+    }
+    if (cube >= 0) {
+        atomicAdd(&a.ress[cube], s1);
+        atomicAdd(&a.ress2[cube], s2);
+    }
+    write_partials<NDIM>(hsum2, hsum2, hist, do_hist, a.partials);
+}
+
+// ---------------------------------------------------------------------------
+// Host-side launchers (one explicit instantiation per integrand TU).
+// ---------------------------------------------------------------------------
+struct EventLaunch {
+    int mode, n_dim;
+    EventKernelArgs k;
+    cudaStream_t stream;
+    int* nblocks_out;
+};
+struct DigestLaunch {
+    int mode, n_dim;
+    DigestKernelArgs k;
+    cudaStream_t stream;
+};
+struct PlusLaunch {
+    int n_dim;
+    PlusKernelArgs k;
+    cudaStream_t stream;
+    int* nblocks_out;
+};
+
+template <class I> int launch_event(const EventLaunch& L);
+template <class I> int launch_digest(const DigestLaunch& L);
+template <class I> int launch_plus(const PlusLaunch& L);
+template <class I> int supported_dim(int n_dim);
+
+// dims with a fused instantiation for the dimension-generic integrands
+#define VF_FOREACH_DIM(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(10) X(12) X(16) X(20)
+
+inline int grid_blocks_for(int64_t n_events, int threads, int min_blocks_per_sm) {
+    const int64_t max_blocks = (int64_t)sm_count() * min_blocks_per_sm;
+    // at least ~4 events per thread before adding blocks
+    int64_t want = (n_events + (int64_t)threads * 4 - 1) / ((int64_t)threads * 4);
+    if (want < 1) want = 1;
+    if (want > max_blocks) want = max_blocks;
+    if (want > kMaxBlocks) want = kMaxBlocks;
+    return (int)want;
+}
+
+template <class I, int NDIM, int MODE>
+int launch_event_dim(const EventLaunch& L) {
+    using C = Cfg<NDIM>;
+    auto kern = event_kernel<I, NDIM, MODE>;
+    const size_t smem = MODE == VF_MODE_VEGAS ? C::kSmemBytes : 0;
+    static bool configured = false;
+    if (!configured) {
+        VF_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)C::kSmemBytes));
+        configured = true;
+    }
+    const int64_t n = (int64_t)(L.k.ev_end - L.k.ev_begin);
+    const int blocks = grid_blocks_for(n, C::kThreads, min_blocks<I, NDIM>());
+    kern<<<blocks, C::kThreads, smem, L.stream>>>(L.k);
+    count_launch();
+    *L.nblocks_out = blocks;
+    VF_CUDA_CHECK(cudaGetLastError());
+    return VF_OK;
+}
+
+template <class I, int NDIM, int MODE>
+int launch_digest_dim(const DigestLaunch& L) {
+    using C = Cfg<NDIM>;
+    auto kern = digest_kernel<I, NDIM, MODE>;
+    static bool configured = false;
+    if (!configured) {
+        VF_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)C::kSmemBytes));
+        configured = true;
+    }
+    const int blocks = grid_blocks_for(L.k.n, C::kThreads, min_blocks<I, NDIM>());
+    kern<<<blocks, C::kThreads, C::kSmemBytes, L.stream>>>(L.k);
+    count_launch();
+    VF_CUDA_CHECK(cudaGetLastError());
+    return VF_OK;
+}
+
+template <class I, int NDIM>
+int launch_plus_dim(const PlusLaunch& L) {
+    using C = Cfg<NDIM>;
+    const bool ext = L.k.rnds != nullptr;
+    auto kern = ext ? plus_event_kernel<I, NDIM, true> : plus_event_kernel<I, NDIM, false>;
+    VF_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)C::kSmemBytes));
+    const int blocks = grid_blocks_for(L.k.n_events, C::kThreads, min_blocks<I, NDIM>());
+    kern<<<blocks, C::kThreads, C::kSmemBytes, L.stream>>>(L.k);
+    count_launch();
+    *L.nblocks_out = blocks;
+    VF_CUDA_CHECK(cudaGetLastError());
+    return VF_OK;
+}
+
+// Instantiates launch_event/launch_digest/launch_plus/supported_dim for integrand I.
+#define VF_DIM_CASE_EVENT(D)                                                              \
+    case D:                                                                               \
+        return L.mode == VF_MODE_VEGAS ? launch_event_dim<I, D, VF_MODE_VEGAS>(L)         \
+                                       : launch_event_dim<I, D, VF_MODE_PLAIN>(L);
+#define VF_DIM_CASE_DIGEST(D)                                                             \
+    case D:                                                                               \
+        return L.mode == VF_MODE_VEGAS ? launch_digest_dim<I, D, VF_MODE_VEGAS>(L)        \
+                                       : launch_digest_dim<I, D, VF_MODE_PLAIN>(L);
+#define VF_DIM_CASE_PLUS(D) \
+    case D:                 \
+        return launch_plus_dim<I, D>(L);
+#define VF_DIM_CASE_SUPPORTED(D) \
+    case D:                      \
+        return 1;
+
+#define VF_INSTANTIATE_GENERIC_INTEGRAND(I_)                                        \
+    template <> int launch_event<I_>(const EventLaunch& L) {                        \
+        using I = I_;                                                               \
+        switch (L.n_dim) { VF_FOREACH_DIM(VF_DIM_CASE_EVENT) default: break; }      \
+        set_error("n_dim=%d has no fused instantiation", L.n_dim);                  \
+        return VF_ERR_UNSUPPORTED;                                                  \
+    }                                                                               \
+    template <> int launch_digest<I_>(const DigestLaunch& L) {                      \
+        using I = I_;                                                               \
+        switch (L.n_dim) { VF_FOREACH_DIM(VF_DIM_CASE_DIGEST) default: break; }     \
+        set_error("n_dim=%d has no fused instantiation", L.n_dim);                  \
+        return VF_ERR_UNSUPPORTED;                                                  \
+    }                                                                               \
+    template <> int launch_plus<I_>(const PlusLaunch& L) {                          \
+        using I = I_;                                                               \
+        switch (L.n_dim) { VF_FOREACH_DIM(VF_DIM_CASE_PLUS) default: break; }       \
+        set_error("n_dim=%d has no fused instantiation", L.n_dim);                  \
+        return VF_ERR_UNSUPPORTED;                                                  \
+    }                                                                               \
+    template <> int supported_dim<I_>(int n_dim) {                                  \
+        switch (n_dim) { VF_FOREACH_DIM(VF_DIM_CASE_SUPPORTED) default: break; }    \
+        return 0;                                                                   \
+    }
+
+#define VF_INSTANTIATE_FIXED_INTEGRAND(I_)                                          \
+    template <> int launch_event<I_>(const EventLaunch& L) {                        \
+        using I = I_;                                                               \
+        switch (L.n_dim) { VF_DIM_CASE_EVENT(I_::kFixedDim) default: break; }       \
+        set_error("integrand needs n_dim=%d, got %d", I_::kFixedDim, L.n_dim);      \
+        return VF_ERR_UNSUPPORTED;                                                  \
+    }                                                                               \
+    template <> int launch_digest<I_>(const DigestLaunch& L) {                      \
+        using I = I_;                                                               \
+        switch (L.n_dim) { VF_DIM_CASE_DIGEST(I_::kFixedDim) default: break; }      \
+        set_error("integrand needs n_dim=%d, got %d", I_::kFixedDim, L.n_dim);      \
+        return VF_ERR_UNSUPPORTED;                                                  \
+    }                                                                               \
+    template <> int launch_plus<I_>(const PlusLaunch& L) {                          \
+        using I = I_;                                                               \
+        switch (L.n_dim) { VF_DIM_CASE_PLUS(I_::kFixedDim) default: break; }        \
+        set_error("integrand needs n_dim=%d, got %d", I_::kFixedDim, L.n_dim);      \
+        return VF_ERR_UNSUPPORTED;                                                  \
+    }                                                                               \
+    template <> int supported_dim<I_>(int n_dim) { return n_dim == I_::kFixedDim; }
+
+}  // namespace vf

@@ -1,0 +1,329 @@
+// Built-in integrands, evaluated inline in the fused event kernel.
+// Every function follows the reference's operation order; the translation
+// units are compiled with -fmad=false so each multiply/add is rounded
+// separately, as TensorFlow's unfused elementwise ops are.
+// Reference citations are file:line relative to /root/reference.
+#pragma once
+#include "vf_common.cuh"
+
+namespace vf {
+
+// ---------------------------------------------------------------------------
+// symgauss, examples/simgauss_tf.py:22-32 (same body tests/test_algs.py:27-36)
+// consts.p[0] = pref = (1/a/sqrt(pi))^d, consts.p[1] = C = sum_{i<=100d} i.
+// The literal "+C ... -C" is kept: it quantises coef to ulp(C).
+// ---------------------------------------------------------------------------
+struct SymGauss {
+    static constexpr int kFixedDim = 0;
+    static constexpr bool kHeavy = false;
+    template <int NDIM>
+    static __device__ __forceinline__ double eval(const double (&x)[NDIM],
+                                                  const IntegrandConsts& c) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < NDIM; ++j) {
+            const double t = __ddiv_rn(__dsub_rn(x[j], 0.5), 0.1);  // :30 (x - 1/2)/a
+            const double q = __dmul_rn(t, t);
+            s = (j == 0) ? q : __dadd_rn(s, q);  // reduce_sum axis=1, left to right
+        }
+        double coef = __dadd_rn(c.p[1], s);  // :29-30
+        coef = __dsub_rn(coef, c.p[1]);      // :31
+        return __dmul_rn(c.p[0], exp(-coef));  // :32
+    }
+};
+
+// product, README.md:63-68 / tests/test_misc.py:24-26
+struct Product {
+    static constexpr int kFixedDim = 0;
+    static constexpr bool kHeavy = false;
+    template <int NDIM>
+    static __device__ __forceinline__ double eval(const double (&x)[NDIM], const IntegrandConsts&) {
+        double p = x[0];
+#pragma unroll
+        for (int j = 1; j < NDIM; ++j) p = __dmul_rn(p, x[j]);
+        return p;
+    }
+};
+
+// ---------------------------------------------------------------------------
+// Spinor helpers shared by the two LO matrix elements
+// (examples/drellyan_lo_tf.py:88-204, examples/singletop_lo_tf.py:105-218).
+// Components that the reference sets to exact complex zero are dropped: adding
+// or multiplying by exact zero does not change the remaining terms.
+// ---------------------------------------------------------------------------
+struct cplx {
+    double re, im;
+};
+__device__ __forceinline__ cplx cmul(cplx a, cplx b) {
+    return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re};
+}
+__device__ __forceinline__ cplx cadd(cplx a, cplx b) { return {a.re + b.re, a.im + b.im}; }
+__device__ __forceinline__ cplx cscale(cplx a, double r) { return {a.re * r, a.im * r}; }  // a*complex(r,0)
+__device__ __forceinline__ cplx cneg(cplx a) { return {-a.re, -a.im}; }
+__device__ __forceinline__ double cabs(cplx a) { return hypot(a.re, a.im); }
+
+struct Mom {
+    double e, x, y, z;
+};
+__device__ __forceinline__ Mom mneg(Mom p) { return {-p.e, -p.x, -p.y, -p.z}; }
+
+struct Angles {
+    double ch, sh;   // cos(theta/2), sin(theta/2)
+    double cp, sp;   // cos(phi), sin(phi)
+    cplx pref;       // sqrt(2)*sqrt(complex(p0,0))
+};
+
+// sqrt(2)*sqrt(complex(p0, 0)): principal branch, +0 imaginary part.
+__device__ __forceinline__ cplx spinor_prefact(double p0) {
+    const double r2 = 1.4142135623730951;  // np.sqrt(2)
+    if (p0 >= 0.0) return {r2 * sqrt(p0), 0.0};
+    return {0.0, r2 * sqrt(-p0)};
+}
+
+__device__ __forceinline__ double clip1(double v) {
+    // tf.where(v < -1, -1, v); tf.where(v > 1, 1, .)  (NaN passes through)
+    double r = v;
+    if (v < -1.0) r = -1.0;
+    if (v > 1.0) r = 1.0;
+    return r;
+}
+
+// theta/phi of drellyan u0 (:93-115) and of ubar0 in both examples
+// (drellyan :140-162, singletop :156-178).
+__device__ __forceinline__ Angles angles_acos(const Mom& p) {
+    const double rz = p.z / p.e;
+    double theta, phi;
+    if (p.x == 0.0) {
+        theta = rz;                    // theta1
+        if (rz > 0.0) theta = 0.0;
+        if (rz < 0.0) theta = M_PI;
+        phi = 0.0;
+    } else {
+        theta = acos(clip1(rz));
+        const double rx = p.x / p.e / sin(theta);
+        phi = acos(clip1(rx));
+        const double ry = p.y / p.e;
+        if (ry < 0.0) phi = -phi;
+    }
+    Angles a;
+    a.ch = cos(theta / 2);
+    a.sh = sin(theta / 2);
+    a.cp = cos(phi);
+    a.sp = sin(phi);
+    a.pref = spinor_prefact(p.e);
+    return a;
+}
+
+// theta/phi of singletop u0 (:110-129): phi in {0, pi} from the sign of px/E.
+__device__ __forceinline__ Angles angles_st_u0(const Mom& p) {
+    const double rz = p.z / p.e;
+    double theta, phi;
+    if (p.x == 0.0) {
+        theta = rz;
+        if (rz > 0.0) theta = 0.0;
+        if (rz < 0.0) theta = M_PI;
+        phi = 0.0;
+    } else {
+        theta = acos(clip1(rz));
+        const double rx = p.x / p.e;
+        phi = (rx < 0.0) ? M_PI : 0.0;
+    }
+    Angles a;
+    a.ch = cos(theta / 2);
+    a.sh = sin(theta / 2);
+    a.cp = cos(phi);
+    a.sp = sin(phi);
+    a.pref = spinor_prefact(p.e);
+    return a;
+}
+
+struct Spin2 {
+    cplx a, b;  // the two non-zero components
+};
+// u0(p, +1): (pref*cos, pref*sin*e^{+i phi}, 0, 0)
+__device__ __forceinline__ Spin2 u0_plus(const Angles& g) {
+    return {cscale(g.pref, g.ch), cmul(cscale(g.pref, g.sh), cplx{g.cp, g.sp})};
+}
+// u0(p, -1): (0, 0, pref*sin*e^{-i phi}, -pref*cos)
+__device__ __forceinline__ Spin2 u0_minus(const Angles& g) {
+    return {cmul(cscale(g.pref, g.sh), cplx{g.cp, -g.sp}), cscale(cneg(g.pref), g.ch)};
+}
+// ubar0(p, -1): (pref*sin*e^{+i phi}, -pref*|cos|, 0, 0)
+__device__ __forceinline__ Spin2 ubar0_minus(const Angles& g) {
+    return {cmul(cscale(g.pref, g.sh), cplx{g.cp, g.sp}), cscale(cneg(g.pref), fabs(g.ch))};
+}
+// ubar0(p, +1): (0, 0, pref*cos, pref*sin*e^{-i phi})
+__device__ __forceinline__ Spin2 ubar0_plus(const Angles& g) {
+    return {cscale(g.pref, g.ch), cmul(cscale(g.pref, g.sh), cplx{g.cp, -g.sp})};
+}
+__device__ __forceinline__ cplx sdot(const Spin2& bra, const Spin2& ket) {
+    return cadd(cmul(bra.a, ket.a), cmul(bra.b, ket.b));
+}
+
+// ---------------------------------------------------------------------------
+// Drell-Yan LO, examples/drellyan_lo_tf.py:27-249 (n_dim = 4)
+// ---------------------------------------------------------------------------
+struct DrellYanLO {
+    static constexpr int kFixedDim = 4;
+    static constexpr bool kHeavy = true;  // register-hungry: one block per SM
+    template <int NDIM>
+    static __device__ double eval(const double (&xa)[NDIM], const IntegrandConsts&) {
+        static_assert(NDIM == 4, "drellyan_lo is 4-dimensional");
+        const double s = 14000.0 * 14000.0;      // :18-22
+        const double conv = 0.3893793e9;         // :24
+        // get_x1x2 :27-41
+        const double kappa = xa[0], y = xa[1];
+        const double logkappa = log(kappa);
+        const double sqrtkappa = sqrt(kappa);
+        const double Ycm = exp(logkappa * (y - 0.5));
+        const double shat = s;
+        const double x1 = sqrtkappa * Ycm;
+        const double x2 = sqrtkappa / Ycm;
+        const double jac = fabs(logkappa);
+        // make_event :44-75
+        const double mV = sqrt(shat * x1 * x2);
+        const double mV2 = mV * mV;
+        const double ecmo2 = mV / 2;
+        const Mom p0{ecmo2, 0.0, 0.0, ecmo2};
+        const Mom p1{ecmo2, 0.0, 0.0, -ecmo2};
+        const Mom pV{p0.e + p1.e, p0.x + p1.x, p0.y + p1.y, p0.z + p1.z};
+        const double YV = 0.5 * log(fabs((pV.e + pV.z) / (pV.e - pV.z)));
+        const double pVt2 = pV.x * pV.x + pV.y * pV.y;
+        const double phi = (2.0 * M_PI) * xa[3];  // :60, 2*np.pi*x3
+        double sphi, cphi;
+        sphi = sin(phi);
+        cphi = cos(phi);
+        const double root = sqrt(mV2 + pVt2);
+        const double ptmax = 0.5 * mV2 / (root - (pV.x * cphi + pV.y * sphi));
+        const double pta = ptmax * xa[2];
+        const double ptx = pta * cphi, pty = pta * sphi;
+        const double Delta = (mV2 + 2 * (pV.x * ptx + pV.y * pty)) / 2.0 / pta / root;
+        const double yy = YV - acosh(Delta);
+        const double kallenF = 2.0 * ptmax / root / fabs(sinh(YV - yy));
+        const Mom p2{pta * cosh(yy), ptx, pty, pta * sinh(yy)};
+        const Mom p3{pV.e - p2.e, pV.x - p2.x, pV.y - p2.y, pV.z - p2.z};
+        double psw = (1.0 / (8.0 * M_PI)) * kallenF;  // :71, 1/(8*np.pi) folded in IEEE
+        psw = psw * jac;
+        const double flux = 1 / (2 * mV2);
+        // qqxllx(-p1, -p0, p2, p3) :207-224
+        const Mom q0 = mneg(p1), q1 = mneg(p0);
+        const Angles a0 = angles_acos(q0), a1 = angles_acos(q1), a2 = angles_acos(p2),
+                     a3 = angles_acos(p3);
+        // za(a,b) = ubar0(a,-1).u0(b,+1); zb(a,b) = ubar0(a,+1).u0(b,-1)
+        const Spin2 ubm0 = ubar0_minus(a0);
+        const cplx za01 = sdot(ubm0, u0_plus(a1));
+        const cplx zb10 = sdot(ubar0_plus(a1), u0_minus(a0));
+        const cplx sp = cmul(za01, zb10);
+        const double lsprod = sp.re;  // sprod(p0,p1) :200-204
+        const cplx za02 = sdot(ubm0, u0_plus(a2));
+        const cplx za03 = sdot(ubm0, u0_plus(a3));
+        const Spin2 u1m = u0_minus(a1);
+        const cplx zb31 = sdot(ubar0_plus(a3), u1m);
+        const cplx zb21 = sdot(ubar0_plus(a2), u1m);
+        const double a = 2 * cabs(cmul(za02, zb31)) / lsprod;
+        const double b = 2 * cabs(cmul(za03, zb21)) / lsprod;
+        const double wgts = 6.0 * (a * a + b * b) / 36.0;
+        // build_luminosity :232-239 with the toy pdf x1*x2 :226-229
+        const double pdf = x1 * x2;
+        const double lumis = (pdf + pdf + pdf + pdf) / x1 / x2;
+        const double lumi_me2 = 2 * lumis * wgts;  // :246
+        return lumi_me2 * psw * flux * conv;       // :247
+    }
+};
+
+// ---------------------------------------------------------------------------
+// single-top LO (t-channel), examples/singletop_lo_tf.py:45-270 (n_dim = 3)
+// ---------------------------------------------------------------------------
+struct SingleTopLO {
+    static constexpr int kFixedDim = 3;
+    static constexpr bool kHeavy = true;
+
+    struct AllSpin {
+        Spin2 up, um, bp, bm;  // u0(+1), u0(-1), ubar0(+1), ubar0(-1)
+    };
+    static __device__ __forceinline__ AllSpin spinors(const Mom& p) {
+        const Angles gu = angles_st_u0(p);
+        const Angles gb = angles_acos(p);
+        return {u0_plus(gu), u0_minus(gu), ubar0_plus(gb), ubar0_minus(gb)};
+    }
+    // sprod(p1,p2) = Re(za(p1,p2)*zb(p2,p1)) :213-218
+    static __device__ __forceinline__ double sprod(const AllSpin& s1, const AllSpin& s2) {
+        const cplx za = sdot(s1.bm, s2.up);
+        const cplx zb = sdot(s2.bp, s1.um);
+        return cmul(za, zb).re;
+    }
+    // qqxtbx :221-230
+    static __device__ __forceinline__ double qqxtbx(const AllSpin& p0, const AllSpin& p1,
+                                                    const AllSpin& p2, const AllSpin& p3,
+                                                    double mt2, double mw2, double gaw2,
+                                                    double gw4) {
+        const double pw2 = sprod(p0, p1);
+        const double d0 = pw2 - mw2;
+        const double wprop = d0 * d0 + mw2 * gaw2;
+        const double a = sprod(p0, p2);
+        const double b = sprod(p0, p3);
+        const double c = sprod(p2, p3);
+        const double d = sprod(p3, p1);
+        return fabs((a + mt2 * b / c) * d) * 9.0 / wprop * gw4 / 36;
+    }
+
+    template <int NDIM>
+    static __device__ double eval(const double (&xa)[NDIM], const IntegrandConsts&) {
+        static_assert(NDIM == 3, "singletop_lo is 3-dimensional");
+        // constants :19-42
+        const double mt = 173.2, sqrts = 8000.0, sqrtsmin = 173.2, mw = 80.419, gaw = 2.1054,
+                     gf = 1.16639e-5;
+        const double mt2 = mt * mt;
+        const double s = sqrts * sqrts;
+        const double smin = sqrtsmin * sqrtsmin;
+        const double bmax = sqrt(1 - smin / s);
+        const double conv = 0.3893793e9;
+        const double gaw2 = gaw * gaw;
+        const double mw2 = mw * mw;
+        const double g = 4 * 1.4142135623730951 * mw2 * gf;
+        const double gw4 = g * g;
+        // get_x1x2 :45-68
+        const double b = bmax * xa[0];
+        const double onemb2 = 1 - b * b;
+        const double shat = smin / onemb2;
+        const double tau = shat / s;
+        const double ymax = -0.5 * log(tau);
+        const double y = ymax * (2 * xa[1] - 1);
+        double jac = 2 * tau * b * bmax / onemb2;
+        jac = jac * (2 * ymax);
+        const double sqrttau = sqrt(tau);
+        const double expy = exp(y);
+        const double x1 = sqrttau * expy;
+        const double x2 = sqrttau / expy;
+        // make_event :71-92
+        const double ecmo2 = sqrt(shat) / 2;
+        const double cc = ecmo2 * (1 - mt2 / shat);
+        const double cosv = 1 - 2 * xa[2];
+        const double sinxi = cc * sqrt(1 - cosv * cosv);
+        const double cosxi = cc * cosv;
+        const Mom p0{ecmo2, 0.0, 0.0, ecmo2};
+        const Mom p1{ecmo2, 0.0, 0.0, -ecmo2};
+        const Mom p2{cc, sinxi, 0.0, cosxi};
+        Mom p3{sqrt(cc * cc + mt2), -sinxi, 0.0, -cosxi};
+        double psw = (1 - mt2 / shat) / (8.0 * M_PI);  // :88
+        psw = psw * jac;
+        const double flux = 1 / (2 * shat);
+        // massless projection :236-239; dot :95-102
+        const double dot30 = p3.e * p0.e - p3.x * p0.x - p3.y * p0.y - p3.z * p0.z;
+        const double k = mt2 / dot30 / 2;
+        p3 = Mom{p3.e - p0.e * k, p3.x - p0.x * k, p3.y - p0.y * k, p3.z - p0.z * k};
+        // channels :242-245
+        const AllSpin A = spinors(p2), B = spinors(mneg(p1)), Cc = spinors(p3),
+                      D = spinors(mneg(p0));
+        const double c1 = qqxtbx(A, B, Cc, D, mt2, mw2, gaw2, gw4);
+        const double c2 = qqxtbx(B, A, Cc, D, mt2, mw2, gaw2, gw4);
+        // luminosities :254-260
+        const double pdf = x1 * x2;
+        const double lumi1 = (pdf + pdf) / x1 / x2;
+        const double lumi2 = (pdf + pdf) / x1 / x2;
+        const double lumi_me2 = 2 * lumi1 * c1 + 2 * lumi2 * c2;  // :267
+        return lumi_me2 * psw * flux * conv;                       // :268
+    }
+};
+
+}  // namespace vf
