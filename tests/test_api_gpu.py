@@ -1,0 +1,325 @@
+"""
+GPU tests of the Python API, mirroring src/vegasflow/tests/test_algs.py and
+test_misc.py of the reference with torch integrands, plus the built-in (fused)
+integrands on independent streams against the oracle.
+"""
+import json
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+import vegasflow_b200 as vf
+from oracle import vegas_ref as R
+from vegasflow_b200 import PlainFlow, VegasFlow, VegasFlowPlus, plain_sampler, vegas_sampler
+
+pytestmark = pytest.mark.gpu
+
+dim = 2
+ncalls = int(1e4)
+n_iter = 4
+
+
+def example_integrand(xarr, weight=None):
+    """symgauss written with torch ops (tests/test_algs.py:27-36)."""
+    n_dim = xarr.shape[-1]
+    a = 0.1
+    n100 = 100 * n_dim
+    pref = pow(1.0 / a / np.sqrt(np.pi), n_dim)
+    coef = float(sum(range(n100 + 1)))
+    coef = coef + torch.sum(torch.square((xarr - 1.0 / 2.0) / a), dim=1)
+    coef = coef - (n100 + 1) * n100 / 2.0
+    return pref * torch.exp(-coef)
+
+
+def instance_and_compile(Integrator, mode=0, integrand_function=example_integrand):
+    if mode == 0:
+        integrand = integrand_function
+    elif mode == 1:
+        def integrand(xarr, n_dim=None):
+            return integrand_function(xarr)
+    elif mode == 2:
+        def integrand(xarr):
+            return integrand_function(xarr)
+    elif mode == 3:
+        def integrand(xarr, n_dim=None, weight=None):
+            return integrand_function(xarr, weight=None)
+    int_instance = Integrator(dim, ncalls, verbose=False)
+    int_instance.set_seed(1000 + 17 * mode + len(Integrator.__name__))  # deterministic streams
+    int_instance.compile(integrand)
+    return int_instance
+
+
+def check_is_one(result, sigmas=3, target_result=1.0):
+    res = result[0]
+    err = np.mean(result[1] * sigmas)
+    np.testing.assert_allclose(res, target_result, atol=err)
+
+
+@pytest.mark.parametrize("mode", range(4))
+def test_VegasFlow(mode):
+    vegas_instance = instance_and_compile(VegasFlow, mode)
+    _ = vegas_instance.run_integration(n_iter)
+    vegas_instance.freeze_grid()
+    result = vegas_instance.run_integration(n_iter)
+    check_is_one(result)
+
+
+def test_VegasFlow_grid_management():
+    vegas_instance = instance_and_compile(VegasFlow, 1)
+    _ = vegas_instance.run_integration(n_iter)
+    vegas_instance.freeze_grid()
+    frozen = vegas_instance.divisions.clone()
+    vegas_instance.n_events = 2 * ncalls
+    check_is_one(vegas_instance.run_integration(n_iter))
+    assert torch.equal(frozen, vegas_instance.divisions)
+    vegas_instance.unfreeze_grid()
+    check_is_one(vegas_instance.run_integration(n_iter))
+    assert not torch.equal(frozen, vegas_instance.divisions)
+    vegas_instance.n_events = 3 * ncalls
+    check_is_one(vegas_instance.run_integration(n_iter))
+
+
+def test_VegasFlow_save_and_load_grid():
+    tmp_filename = tempfile.mktemp()
+    vegas_instance = instance_and_compile(VegasFlow)
+    _ = vegas_instance.run_integration(1)
+    current_grid = vegas_instance.divisions.cpu().numpy()
+    assert not np.array_equal(current_grid, R.initial_divisions(dim))
+    vegas_instance.save_grid(tmp_filename)
+    with open(tmp_filename, "r") as f:
+        json_grid = np.array(json.load(f)["grid"])
+    np.testing.assert_equal(current_grid, json_grid)
+    tmp_grid = np.sort(np.random.rand(*current_grid.shape), axis=1)
+    vegas_instance.load_grid(numpy_grid=tmp_grid)
+    np.testing.assert_equal(vegas_instance.divisions.cpu().numpy(), tmp_grid)
+
+
+@pytest.mark.parametrize("mode", range(4))
+def test_PlainFlow(mode):
+    plain_instance = instance_and_compile(PlainFlow, mode)
+    check_is_one(plain_instance.run_integration(n_iter))
+
+
+def test_PlainFlow_change_nevents():
+    plain_instance = instance_and_compile(PlainFlow, 0)
+    check_is_one(plain_instance.run_integration(n_iter))
+    plain_instance.n_events = 2 * ncalls
+    check_is_one(plain_instance.run_integration(n_iter))
+
+
+def helper_rng_tester(sampling_function, n_events):
+    rnds, px = sampling_function(n_events)
+    np.testing.assert_equal(tuple(rnds.shape), (n_events, dim))
+    return rnds, px
+
+
+def test_rng_generation_plain(n_events=100):
+    inst = instance_and_compile(PlainFlow)
+    _, px = helper_rng_tester(inst.generate_random_array, n_events)
+    np.testing.assert_equal(px.cpu().numpy(), 1.0 / n_events)
+
+
+def test_rng_generation_vegasflow(n_events=100):
+    inst = instance_and_compile(VegasFlow)
+    inst.run_integration(2)
+    a, px = helper_rng_tester(inst.generate_random_array, n_events)
+    np.testing.assert_equal(tuple(px.shape), (n_events,))
+    b, _ = inst.generate_random_array(n_events)
+    assert not torch.equal(a, b)  # successive calls use fresh streams
+    # p(x) integrates to one: mean of 1/(n p) ... sum of px over samples of the unit volume
+    x, p = inst.generate_random_array(200000)
+    assert abs(float(p.sum()) - 1.0) < 0.05
+
+
+def test_rng_generation_vegasflowplus(n_events=100):
+    inst = instance_and_compile(VegasFlowPlus)
+    _, px = helper_rng_tester(inst.generate_random_array, n_events)
+    np.testing.assert_equal(tuple(px.shape), (n_events,))
+    _, px = helper_rng_tester(inst.generate_random_array, 3 * inst.n_events + 17)
+
+
+def test_rng_generation_wrappers(n_events=100):
+    p = plain_sampler(example_integrand, dim, n_events, training_steps=2, return_class=True)
+    _ = helper_rng_tester(p.generate_random_array, n_events)
+    v = vegas_sampler(example_integrand, dim, n_events, training_steps=2)
+    _ = helper_rng_tester(v, n_events)
+
+
+@pytest.mark.parametrize("mode", range(4))
+def test_VegasFlowPlus_default(mode):
+    inst = instance_and_compile(VegasFlowPlus, mode)
+    check_is_one(inst.run_integration(n_iter))
+
+
+def test_VegasFlowPlus_adaptive_python_integrand():
+    inst = VegasFlowPlus(dim, ncalls, adaptive=True, verbose=False)
+    inst.set_seed(79)
+    inst.compile(example_integrand)
+    check_is_one(inst.run_integration(n_iter))
+    assert int(inst.n_ev.sum()) == inst.n_events
+
+
+# ---- tests/test_misc.py ------------------------------------------------------
+def _vector_integrand(xarr, weight=None):
+    res = torch.square((xarr - 1.0) ** 2)
+    return torch.exp(-res) / 0.845
+
+
+def _wrong_integrand(xarr):
+    return torch.sum(xarr)
+
+
+def _simple_integrand(xarr):
+    return torch.prod(xarr, dim=1)
+
+
+def _simple_integral(xmin, xmax):
+    xm = np.array(xmin) ** 2 / 2.0
+    xp = np.array(xmax) ** 2 / 2.0
+    return np.prod(xp - xm)
+
+
+def _wrong_vector_integrand(xarr):
+    return xarr.T
+
+
+@pytest.mark.parametrize("mode", range(4))
+@pytest.mark.parametrize("alg", [VegasFlow, PlainFlow])
+def test_working_vectorial(alg, mode):
+    inst = instance_and_compile(alg, mode=mode, integrand_function=_vector_integrand)
+    result = inst.run_integration(2)
+    assert result[0].shape == (dim,)
+    check_is_one(result, sigmas=5)
+
+
+def test_notworking_vectorial():
+    with pytest.raises(NotImplementedError):
+        _ = instance_and_compile(VegasFlowPlus, integrand_function=_vector_integrand)
+
+
+def test_check_wrong_main_dimension():
+    inst = VegasFlow(3, 100, main_dimension=5, verbose=False)
+    with pytest.raises(ValueError):
+        inst.compile(_vector_integrand)
+
+
+@pytest.mark.parametrize("wrong_fun", [_wrong_vector_integrand, _wrong_integrand])
+def test_wrong_shape(wrong_fun):
+    with pytest.raises(ValueError):
+        _ = instance_and_compile(PlainFlow, integrand_function=wrong_fun)
+
+
+@pytest.mark.parametrize("alg", [PlainFlow, VegasFlow, VegasFlowPlus])
+@pytest.mark.parametrize("builtin", [False, True])
+def test_integration_limits(alg, builtin, ncalls=int(1e4)):
+    rng = np.random.default_rng(len(alg.__name__) * 2 + int(builtin))
+    dims = int(rng.integers(1, 5))
+    xmin = -1.0 + rng.random(dims) * 2.0
+    xmax = 3.0 + rng.random(dims)
+    inst = alg(dims, ncalls, xmin=xmin, xmax=xmax, verbose=False)
+    inst.set_seed(4242 + dims)
+    inst.compile(vf.integrands.product if builtin else _simple_integrand)
+    result = inst.run_integration(5)
+    check_is_one(result, target_result=_simple_integral(xmin, xmax))
+
+
+# ---- built-in (fused) integrands ---------------------------------------------
+@pytest.mark.parametrize("alg", [PlainFlow, VegasFlow, VegasFlowPlus])
+def test_fused_symgauss_is_one(alg):
+    inst = alg(dim, ncalls, verbose=False)
+    inst.set_seed(77)
+    inst.compile(vf.integrands.symgauss)
+    check_is_one(inst.run_integration(n_iter))
+    assert len(inst.history) == n_iter and all(len(h) == 3 for h in inst.history)
+    assert all(isinstance(h[0], float) for h in inst.history)
+
+
+def test_fused_vegasflowplus_adaptive():
+    inst = VegasFlowPlus(4, 200000, adaptive=True, verbose=False)
+    inst.set_seed(78)
+    inst.compile("symgauss")
+    before = inst.n_ev.clone().cpu()
+    check_is_one(inst.run_integration(5))
+    assert not torch.equal(before, inst.n_ev.cpu())  # samples were redistributed
+    assert int(inst.n_ev.sum()) == inst.n_events
+    assert int(inst.n_ev.min()) >= inst.min_neval_hcube
+
+
+def test_vegas_wrapper_configs_1_and_2():
+    """BASELINE configs[0] and a reduced configs[1] through the convenience wrapper."""
+    res, err = vf.vegas_wrapper(vf.integrands.symgauss, 4, 5, int(1e6))
+    assert abs(res - 1.0) < 3 * err and err < 5e-4
+    res, err = vf.vegas_wrapper(vf.integrands.product, 8, 5, int(1e6))
+    assert abs(res - 2.0**-8) < 3 * err and err < 2e-6
+
+
+def test_independent_stream_agreement_with_oracle():
+    """Independent streams: integral within 3 combined sigma of the oracle's, refined grids
+    within 3x the oracle-vs-oracle (two seeds) noise floor at the same N."""
+    d, n, iters = 4, 200000, 5
+    inst = VegasFlow(d, n, verbose=False)
+    inst.set_seed(5)
+    inst.compile(vf.integrands.symgauss)
+    res, err = inst.run_integration(iters)
+    o_res, o_err, _, grid_a = R.vegas_integrate(R.symgauss, d, n, iters, R.uniform_source_numpy(1))
+    _, _, _, grid_b = R.vegas_integrate(R.symgauss, d, n, iters, R.uniform_source_numpy(2))
+    assert abs(res - o_res) < 3 * np.hypot(err, o_err)
+    assert 0.5 < err / o_err < 2.0
+    noise = np.abs(grid_a - grid_b).max()
+    assert np.abs(inst.divisions.cpu().numpy() - grid_a).max() < 3 * noise + 1e-4
+
+
+def test_singletop_and_drellyan_fused():
+    res, err = vf.vegas_wrapper(vf.integrands.singletop_lo, 3, 5, int(1e6))
+    assert abs(res - 423.9) < 4 * err + 0.5
+    # Drell-Yan: ln^2-divergent at kappa -> 0: only finiteness/positivity is checked
+    inst = VegasFlow(4, int(2e5), verbose=False)
+    inst.compile(vf.integrands.drellyan_lo)
+    r, e = inst.run_integration(3)
+    assert np.isfinite(r) and r > 0 and np.isfinite(e)
+
+
+def test_seed_reproducibility_and_instance_independence():
+    def run(seed):
+        inst = VegasFlow(3, 50000, verbose=False)
+        if seed is not None:
+            inst.set_seed(seed)
+        inst.compile(vf.integrands.product)
+        return inst.run_integration(3)
+
+    # same seed -> same events.  The scalar reductions run in a fixed order; the histogram bins
+    # are summed by shared-memory atomics, so the refined grid (hence later iterations) can
+    # differ in the last bits between runs.
+    a, b = run(3), run(3)
+    assert abs(a[0] - b[0]) <= 1e-10 * abs(a[0]) and abs(a[1] - b[1]) <= 1e-8 * a[1]
+    assert run(3) != run(4)
+    assert run(None) != run(None)  # two default instances use different Philox keys
+
+
+def test_run_before_compile_raises():
+    inst = VegasFlow(2, 100, verbose=False)
+    with pytest.raises(RuntimeError, match="Compile must be ran"):
+        inst.run_integration(1)
+    with pytest.raises(NotImplementedError):
+        inst.make_differentiable()
+
+
+def test_utils_consume_array_into_indices_gpu():
+    """src/vegasflow/tests/test_utils.py:11-30 on CUDA tensors."""
+    from vegasflow_b200.utils import consume_array_into_indices, py_consume_array_into_indices
+
+    size_in = np.random.randint(5, 100)
+    size_out = np.random.randint(1, size_in - 3)
+    input_array = np.random.rand(size_in)
+    indices = np.random.randint(0, size_out, size=size_in)
+    t_in = torch.from_numpy(input_array).cuda()
+    t_idx = torch.from_numpy(indices.reshape(-1, 1)).cuda()
+    result = consume_array_into_indices(t_in, t_idx, size_out).cpu().numpy()
+    py_result = py_consume_array_into_indices(t_in, t_idx, size_out).cpu().numpy()
+    np.testing.assert_allclose(result, py_result, rtol=1e-14)  # index_add order is free
+    check_result = np.zeros(size_out)
+    for val, i in zip(input_array, indices):
+        check_result[i] += val
+    np.testing.assert_allclose(check_result, result)

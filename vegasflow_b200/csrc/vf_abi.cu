@@ -183,8 +183,7 @@ int vf_run_event(int mode, int integrand, int n_dim, uint64_t ev_begin, int64_t 
     L.k.ev_begin = ev_begin;
     L.k.ev_end = ev_begin + (uint64_t)n_events;
     L.k.xjac = xjac;
-    L.k.seed_lo = (uint32_t)seed;
-    L.k.seed_hi = (uint32_t)(seed >> 32);
+    L.k.pk = make_philox_keys(seed);
     L.k.iteration = iteration;
     L.k.train = train;
     rc = dispatch_integrand(integrand, [&](auto tag) { return launch_event<decltype(tag)>(L); });
@@ -334,8 +333,7 @@ int vfp_run_event(int integrand, int n_dim, int n_strat, int64_t n_cubes, int64_
     L.k.n_events = n_events;
     L.k.n_strat = n_strat;
     L.k.xjac = xjac;
-    L.k.seed_lo = (uint32_t)seed;
-    L.k.seed_hi = (uint32_t)(seed >> 32);
+    L.k.pk = make_philox_keys(seed);
     L.k.iteration = iteration;
     L.k.train = train;
     rc = dispatch_integrand(integrand, [&](auto tag) { return launch_plus<decltype(tag)>(L); });

@@ -181,14 +181,14 @@ int launch_epilogue(int n_dim, int64_t n_events, int train, const double* sums, 
 // Engine uniforms (for tests / samplers): rnds[n][n_dim].
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) uniforms_kernel(int n_dim, uint64_t ev_begin, int64_t n,
-                                                       uint32_t seed_lo, uint32_t seed_hi,
+                                                       const __grid_constant__ PhiloxKeys pk,
                                                        uint32_t iteration, double* rnds) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x) {
         const uint64_t e = ev_begin + (uint64_t)i;
         for (int p = 0; 2 * p < n_dim; ++p) {
             const uint4 o = philox4x32_10((uint32_t)e, (uint32_t)(e >> 32), (uint32_t)p, iteration,
-                                          seed_lo, seed_hi);
+                                          pk);
             rnds[i * n_dim + 2 * p] = u52_to_uniform(o.x, o.y);
             if (2 * p + 1 < n_dim) rnds[i * n_dim + 2 * p + 1] = u52_to_uniform(o.z, o.w);
         }
@@ -199,8 +199,8 @@ int launch_uniforms(int n_dim, uint64_t ev_begin, int64_t n, uint64_t seed, uint
                     double* rnds, cudaStream_t stream) {
     if (n <= 0) return VF_OK;
     const int blocks = (int)imin64((n + 255) / 256, (int64_t)sm_count() * 8);
-    uniforms_kernel<<<blocks, 256, 0, stream>>>(n_dim, ev_begin, n, (uint32_t)seed,
-                                                (uint32_t)(seed >> 32), iteration, rnds);
+    uniforms_kernel<<<blocks, 256, 0, stream>>>(n_dim, ev_begin, n, make_philox_keys(seed),
+                                                iteration, rnds);
     count_launch();
     VF_CUDA_CHECK(cudaGetLastError());
     return VF_OK;
@@ -211,8 +211,9 @@ int launch_uniforms(int n_dim, uint64_t ev_begin, int64_t n, uint64_t seed, uint
 // any n_dim <= kMaxDim, grid table staged once per block (single copy).
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) sample_kernel(int mode, int n_dim, uint64_t ev_begin,
-                                                     int64_t n, double xjac, uint32_t seed_lo,
-                                                     uint32_t seed_hi, uint32_t iteration,
+                                                     int64_t n, double xjac,
+                                                     const __grid_constant__ PhiloxKeys pk,
+                                                     uint32_t iteration,
                                                      const double* __restrict__ divisions,
                                                      const __grid_constant__ Limits lim, double* x,
                                                      double* w, int32_t* ind) {
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(256) sample_kernel(int mode, int n_dim, uint64
         double wt = 1.0;
         for (int p = 0; 2 * p < n_dim; ++p) {
             const uint4 o = philox4x32_10((uint32_t)e, (uint32_t)(e >> 32), (uint32_t)p, iteration,
-                                          seed_lo, seed_hi);
+                                          pk);
             for (int h = 0; h < 2; ++h) {
                 const int j = 2 * p + h;
                 if (j >= n_dim) break;
@@ -242,7 +243,8 @@ __global__ void __launch_bounds__(256) sample_kernel(int mode, int n_dim, uint64
                 if (mode == VF_MODE_VEGAS) {
                     const double xn = __dmul_rn(kFBins, __dsub_rn(1.0, r));
                     double wfac;
-                    vegas_map_dim<1>(xn, tbl + j * kBins, 0, xv, wfac, bin);
+                    vegas_map_dim<1>(xn, reinterpret_cast<const char*>(tbl + j * kBins), xv, wfac,
+                                     bin);
                     wt = (j == 0) ? wfac : __dmul_rn(wt, wfac);
                 } else {
                     xv = r;
@@ -264,8 +266,8 @@ int launch_sample(int mode, int n_dim, uint64_t ev_begin, int64_t n, double xjac
     if (n <= 0) return VF_OK;
     const int blocks = (int)imin64((n + 255) / 256, (int64_t)sm_count() * 8);
     const size_t smem = mode == VF_MODE_VEGAS ? (size_t)n_dim * kBins * 16 : 0;
-    sample_kernel<<<blocks, 256, smem, stream>>>(mode, n_dim, ev_begin, n, xjac, (uint32_t)seed,
-                                                 (uint32_t)(seed >> 32), iteration, divisions, lim,
+    sample_kernel<<<blocks, 256, smem, stream>>>(mode, n_dim, ev_begin, n, xjac,
+                                                 make_philox_keys(seed), iteration, divisions, lim,
                                                  x, w, ind);
     count_launch();
     VF_CUDA_CHECK(cudaGetLastError());

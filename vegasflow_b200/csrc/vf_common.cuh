@@ -52,20 +52,37 @@ constexpr uint32_t kPhiloxM1 = 0xCD9E8D57u;
 constexpr uint32_t kPhiloxW0 = 0x9E3779B9u;
 constexpr uint32_t kPhiloxW1 = 0xBB67AE85u;
 
-__host__ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2,
-                                                        uint32_t c3, uint32_t k0, uint32_t k1) {
+// Round keys k_r = key + r*(W0, W1) depend only on the seed: they are expanded once on the
+// host and travel in kernel-parameter (constant) space, so the per-event rounds cost exactly
+// two IMAD.WIDE + two LOP3 each.
+struct PhiloxKeys {
+    uint32_t k0[10];
+    uint32_t k1[10];
+};
+inline PhiloxKeys make_philox_keys(uint64_t seed) {
+    PhiloxKeys pk;
+    uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+        pk.k0[r] = a;
+        pk.k1[r] = b;
+        a += kPhiloxW0;
+        b += kPhiloxW1;
+    }
+    return pk;
+}
+
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                               const PhiloxKeys& pk) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         const uint64_t p0 = (uint64_t)kPhiloxM0 * c0;
         const uint64_t p1 = (uint64_t)kPhiloxM1 * c2;
-        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
-        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ pk.k0[r];
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ pk.k1[r];
         c1 = (uint32_t)p1;
         c3 = (uint32_t)p0;
         c0 = n0;
         c2 = n2;
-        k0 += kPhiloxW0;
-        k1 += kPhiloxW1;
     }
     return make_uint4(c0, c1, c2, c3);
 }
@@ -86,7 +103,7 @@ __device__ __forceinline__ double u52_to_uniform(uint32_t hi, uint32_t lo) {
 // evaluated once per bin when the table is staged -- same IEEE operation on
 // the same operands as the per-event form.
 template <int TC>
-__device__ __forceinline__ void vegas_map_dim(double xn, const double2* __restrict__ tbl, int slot,
+__device__ __forceinline__ void vegas_map_dim(double xn, const char* __restrict__ tbl_lane,
                                               double& x, double& wfac, int& bin) {
     // floor via round-down add of 2^52: t = floor(xn) + 2^52 exactly for 0 <= xn < 2^31;
     // the integer sits in the low mantissa word (== C truncation, vflow.py:67).
@@ -94,7 +111,8 @@ __device__ __forceinline__ void vegas_map_dim(double xn, const double2* __restri
     bin = __double2loint(t);
     const double fl = __dsub_rn(t, kTwo52);   // tf.math.floor(xn), vflow.py:75
     const double aux = __dsub_rn(xn, fl);     // :75
-    const double2 e = tbl[bin * TC + slot];
+    // tbl_lane already includes this lane's copy slot and the dimension offset
+    const double2 e = *reinterpret_cast<const double2*>(tbl_lane + bin * (TC * 16));
     x = __dadd_rn(e.x, __dmul_rn(e.y, aux));  // :76, mul then add
     wfac = __dmul_rn(e.y, kFBins);            // :78
 }

@@ -35,8 +35,9 @@ struct EventKernelArgs {
     double* partials;         // [gridDim.x][2 + NDIM*50]
     uint64_t ev_begin, ev_end;
     double xjac;
-    uint32_t seed_lo, seed_hi, iteration;
+    uint32_t iteration;
     int train;
+    PhiloxKeys pk;
     Limits lim;
     IntegrandConsts ic;
 };
@@ -102,6 +103,37 @@ __device__ __forceinline__ void write_partials(double sum, double sum2, const do
     }
 }
 
+// Histogram update of one event: hist[j][bin_j][slot] += tmp2 for every dimension
+// (vflow.py:370-387, utils.py:40-43).  Shared memory has no native fp64 add, so each update is
+// a compare-and-swap; the d loads, adds and CAS are issued back to back (independent
+// addresses) and only the lanes whose CAS lost a race -- same bin as lane+HC, or another warp
+// -- fall into the retry loop.
+template <int NDIM>
+__device__ __forceinline__ void hist_update(char* hist_lane, const int (&bin)[NDIM], double tmp2) {
+    using C = Cfg<NDIM>;
+    unsigned long long* addr[NDIM];
+    unsigned long long old[NDIM];
+#pragma unroll
+    for (int j = 0; j < NDIM; ++j) {
+        addr[j] = reinterpret_cast<unsigned long long*>(hist_lane + j * (kBins * C::HC * 8) +
+                                                        bin[j] * (C::HC * 8));
+        old[j] = *reinterpret_cast<volatile unsigned long long*>(addr[j]);
+    }
+    unsigned long long seen[NDIM];
+    unsigned long long lost = 0;
+#pragma unroll
+    for (int j = 0; j < NDIM; ++j) {
+        const double upd = __longlong_as_double((long long)old[j]) + tmp2;
+        seen[j] = atomicCAS(addr[j], old[j], (unsigned long long)__double_as_longlong(upd));
+        lost |= seen[j] ^ old[j];
+    }
+    if (lost) {
+#pragma unroll
+        for (int j = 0; j < NDIM; ++j)
+            if (seen[j] != old[j]) atomicAdd(reinterpret_cast<double*>(addr[j]), tmp2);
+    }
+}
+
 // ---------------------------------------------------------------------------
 // K1: fused event kernel (VegasFlow._run_event, vflow.py:389-430; PlainFlow
 // plain.py:18-35).  Thread t evaluates global events ev_begin + t, + stride...
@@ -119,7 +151,8 @@ event_kernel(const __grid_constant__ EventKernelArgs a) {
         __syncthreads();
     }
     const int lane = threadIdx.x & 31;
-    const int tslot = lane % C::TC, hslot = lane % C::HC;
+    const char* tbl_lane = reinterpret_cast<const char*>(tbl) + (lane % C::TC) * 16;
+    char* hist_lane = reinterpret_cast<char*>(hist) + (lane % C::HC) * 8;
     double sum = 0.0, sum2 = 0.0;
     const uint64_t stride = (uint64_t)gridDim.x * C::kThreads;
     for (uint64_t n = a.ev_begin + (uint64_t)blockIdx.x * C::kThreads + threadIdx.x; n < a.ev_end;
@@ -130,7 +163,7 @@ event_kernel(const __grid_constant__ EventKernelArgs a) {
 #pragma unroll
         for (int p = 0; p < (NDIM + 1) / 2; ++p) {
             const uint4 o = philox4x32_10((uint32_t)n, (uint32_t)(n >> 32), (uint32_t)p,
-                                          a.iteration, a.seed_lo, a.seed_hi);
+                                          a.iteration, a.pk);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int j = 2 * p + h;
@@ -139,7 +172,7 @@ event_kernel(const __grid_constant__ EventKernelArgs a) {
                     if (MODE == VF_MODE_VEGAS) {
                         const double xn = __dmul_rn(kFBins, __dsub_rn(1.0, r));  // vflow.py:117
                         double wfac;
-                        vegas_map_dim<C::TC>(xn, tbl + j * kBins * C::TC, tslot, x[j], wfac,
+                        vegas_map_dim<C::TC>(xn, tbl_lane + j * (kBins * C::TC * 16), x[j], wfac,
                                              bin[j]);
                         w = (j == 0) ? wfac : __dmul_rn(w, wfac);  // reduce_prod, vflow.py:78
                     } else {
@@ -154,11 +187,7 @@ event_kernel(const __grid_constant__ EventKernelArgs a) {
         const double tmp2 = __dmul_rn(tmp, tmp);           // vflow.py:417
         sum += tmp;                                        // vflow.py:420
         sum2 += tmp2;                                      // vflow.py:421
-        if (do_hist) {                                     // vflow.py:370-387, utils.py:40-43
-#pragma unroll
-            for (int j = 0; j < NDIM; ++j)
-                atomicAdd(&hist[(j * kBins + bin[j]) * C::HC + hslot], tmp2);
-        }
+        if (do_hist) hist_update<NDIM>(hist_lane, bin, tmp2);
     }
     write_partials<NDIM>(sum, sum2, hist, do_hist, a.partials);
 }
@@ -189,7 +218,7 @@ digest_kernel(const __grid_constant__ DigestKernelArgs a) {
         stage_grid<NDIM>(a.divisions, tbl, nullptr, false);
         __syncthreads();
     }
-    const int tslot = (threadIdx.x & 31) % C::TC;
+    const char* tbl_lane = reinterpret_cast<const char*>(tbl) + ((threadIdx.x & 31) % C::TC) * 16;
     for (int64_t n = (int64_t)blockIdx.x * C::kThreads + threadIdx.x; n < a.n;
          n += (int64_t)gridDim.x * C::kThreads) {
         double x[NDIM];
@@ -201,7 +230,7 @@ digest_kernel(const __grid_constant__ DigestKernelArgs a) {
             if (MODE == VF_MODE_VEGAS) {
                 const double xn = __dmul_rn(kFBins, __dsub_rn(1.0, r));
                 double wfac;
-                vegas_map_dim<C::TC>(xn, tbl + j * kBins * C::TC, tslot, x[j], wfac, bin[j]);
+                vegas_map_dim<C::TC>(xn, tbl_lane + j * (kBins * C::TC * 16), x[j], wfac, bin[j]);
                 w = (j == 0) ? wfac : __dmul_rn(w, wfac);
             } else {
                 x[j] = r;
@@ -243,8 +272,9 @@ struct PlusKernelArgs {
     int64_t n_cubes, n_events;
     int n_strat;
     double xjac;
-    uint32_t seed_lo, seed_hi, iteration;
+    uint32_t iteration;
     int train;
+    PhiloxKeys pk;
     Limits lim;
     IntegrandConsts ic;
 };
@@ -260,7 +290,8 @@ plus_event_kernel(const __grid_constant__ PlusKernelArgs a) {
     stage_grid<NDIM>(a.divisions, tbl, hist, do_hist);
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    const int tslot = lane % C::TC, hslot = lane % C::HC;
+    const char* tbl_lane = reinterpret_cast<const char*>(tbl) + (lane % C::TC) * 16;
+    char* hist_lane = reinterpret_cast<char*>(hist) + (lane % C::HC) * 8;
     const int64_t per_block = (a.n_events + gridDim.x - 1) / gridDim.x;
     const int64_t begin = (int64_t)blockIdx.x * per_block;
     const int64_t end = min(begin + per_block, a.n_events);
@@ -303,7 +334,7 @@ plus_event_kernel(const __grid_constant__ PlusKernelArgs a) {
             uint4 o;
             if (!EXT)
                 o = philox4x32_10((uint32_t)e, (uint32_t)((uint64_t)e >> 32), (uint32_t)p,
-                                  a.iteration, a.seed_lo, a.seed_hi);
+                                  a.iteration, a.pk);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int j = 2 * p + h;
@@ -315,7 +346,8 @@ plus_event_kernel(const __grid_constant__ PlusKernelArgs a) {
                     const double xn =
                         __ddiv_rn(__dmul_rn(__dadd_rn(coords[j], r), kFBins), fstrat);
                     double wfac;
-                    vegas_map_dim<C::TC>(xn, tbl + j * kBins * C::TC, tslot, x[j], wfac, bin[j]);
+                    vegas_map_dim<C::TC>(xn, tbl_lane + j * (kBins * C::TC * 16), x[j], wfac,
+                                         bin[j]);
                     w = (j == 0) ? wfac : __dmul_rn(w, wfac);
                 }
             }
@@ -327,11 +359,7 @@ plus_event_kernel(const __grid_constant__ PlusKernelArgs a) {
         const double tmp2 = __dmul_rn(tmp, tmp);  // vflowplus.py:210
         s1 += tmp;
         s2 += tmp2;
-        if (do_hist) {
-#pragma unroll
-            for (int j = 0; j < NDIM; ++j)
-                atomicAdd(&hist[(j * kBins + bin[j]) * C::HC + hslot], tmp2);
-        }
+        if (do_hist) hist_update<NDIM>(hist_lane, bin, tmp2);
         if (EXT) {
 #pragma unroll
             for (int j = 0; j < NDIM; ++j) {

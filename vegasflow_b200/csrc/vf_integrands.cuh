@@ -13,6 +13,45 @@ namespace vf {
 // consts.p[0] = pref = (1/a/sqrt(pi))^d, consts.p[1] = C = sum_{i<=100d} i.
 // The literal "+C ... -C" is kept: it quantises coef to ulp(C).
 // ---------------------------------------------------------------------------
+// y / 0.1 with IEEE round-to-nearest in three fp64 operations instead of the ~14 of the
+// generic division: q0 = rn(10*y) is within 1 ulp of y/a (10 = rn(1/a) and 1/a = 10*(1-2^-54...)),
+// the residual r = y - a*q0 is exact in one FMA, and q0 + 10*r rounds correctly (Markstein).
+// Checked against `/` on 4e8 values on the host and by the parity tests.
+__device__ __forceinline__ double div_by_tenth(double y) {
+    const double q0 = __dmul_rn(y, 10.0);
+    const double r = __fma_rn(-0.1, q0, y);
+    return __fma_rn(r, 10.0, q0);
+}
+
+// exp(x) for x <= 0 (symgauss always calls exp(-coef) with coef >= 0).  Cody-Waite reduction
+// x = k*ln2 + r, |r| <= ln2/2, degree-11 near-minimax polynomial (Chebyshev interpolant of
+// (e^r-1-r)/r^2, approximation error 0.14 ulp; derivation in DESIGN.md), scaling by an exponent
+// add.  Coefficients sit in constant memory so each Horner step is one DFMA with a constant-bank
+// operand.  Total error ~1 ulp, i.e. the same class as libm/libdevice exp.
+static __constant__ double kExpCoef[12] = {
+    1.0, 1.0, 0.5000000000000001, 0.16666666666666669, 0.041666666666624164,
+    0.008333333333330065, 0.0013888888917196719, 0.00019841269863040545,
+    2.4801521322368692e-05, 2.7557268480310024e-06, 2.7620075879983367e-07,
+    2.5100375832561234e-08};
+
+__device__ __forceinline__ double exp_nonpositive(double x) {
+    const double kMagic = 6755399441055744.0;  // 1.5 * 2^52: round-to-nearest-integer add
+    const double t = fma(x, 1.4426950408889634, kMagic);
+    const int k = __double2loint(t);
+    const double kf = t - kMagic;
+    double r = fma(kf, -6.93147180559945286e-01, x);
+    r = fma(kf, -2.31904681384629956e-17, r);
+    double p = kExpCoef[11];
+#pragma unroll
+    for (int i = 10; i >= 0; --i) p = fma(p, r, kExpCoef[i]);
+    if (x < -700.0) {  // result below 2^-1009: two-step scaling through the subnormal range
+        if (x < -800.0) return 0.0;
+        const double q = __hiloint2double(__double2hiint(p) + ((k + 256) << 20), __double2loint(p));
+        return q * 8.636168555094445e-78;  // 2^-256
+    }
+    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
+}
+
 struct SymGauss {
     static constexpr int kFixedDim = 0;
     static constexpr bool kHeavy = false;
@@ -22,13 +61,13 @@ struct SymGauss {
         double s = 0.0;
 #pragma unroll
         for (int j = 0; j < NDIM; ++j) {
-            const double t = __ddiv_rn(__dsub_rn(x[j], 0.5), 0.1);  // :30 (x - 1/2)/a
+            const double t = div_by_tenth(__dsub_rn(x[j], 0.5));  // :30 (x - 1/2)/a, a = 0.1
             const double q = __dmul_rn(t, t);
             s = (j == 0) ? q : __dadd_rn(s, q);  // reduce_sum axis=1, left to right
         }
         double coef = __dadd_rn(c.p[1], s);  // :29-30
         coef = __dsub_rn(coef, c.p[1]);      // :31
-        return __dmul_rn(c.p[0], exp(-coef));  // :32
+        return __dmul_rn(c.p[0], exp_nonpositive(-coef));  // :32
     }
 };
 

@@ -272,6 +272,13 @@ class MonteCarloFlow(ABC):
         buffer is then all-reduced over ranks.
         Unfused path: chunks of `events_per_run` as in the reference.
         """
+        out = self._launch_events(**kwargs)
+        self._allreduce(out)
+        self._iteration += 1
+        return out
+
+    def _launch_events(self, **kwargs):
+        """Enqueue this rank's share of the iteration's events (no collective)."""
         if not self.event:
             raise RuntimeError("Compile must be ran before running any iterations")
         self._ensure_device()
@@ -291,8 +298,6 @@ class MonteCarloFlow(ABC):
                                  **kwargs)
                 first = False
                 done += ncalls
-        self._allreduce(out)
-        self._iteration += 1
         return out
 
     def _allreduce(self, out):

@@ -66,6 +66,9 @@ class PlainFlow(MonteCarloFlow):
     def _run_iteration(self):
         """plain.py:37-43"""
         self.run_event()
+        return self._iteration_epilogue()
+
+    def _iteration_epilogue(self):
         if self._vectorial:
             res, raw_res2 = self._vec_acc
             n = float(self.n_events)

@@ -208,7 +208,12 @@ class VegasFlow(MonteCarloFlow):
 
     def _iteration_content(self):
         """Steps to follow per iteration (vflow.py:432-442)"""
-        res, res2, _ = self.run_event()
+        self.run_event()
+        return self._iteration_epilogue()
+
+    def _iteration_epilogue(self):
+        """sigma (vflow.py:437-438) and grid refinement (vflow.py:440-441) of the iteration
+        whose reduced sums/histogram sit in the packed buffer."""
         if self._vectorial:
             res, res2 = self._vec_acc
             n = float(self.n_events)

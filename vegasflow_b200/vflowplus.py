@@ -221,17 +221,25 @@ class VegasFlowPlus(VegasFlow):
     def run_event(self, tensorize_events=None, **kwargs):
         """VegasFlowPlus is single-device like the reference (vflowplus.py:88-100,
         244-247): the whole iteration is one launch, no sharding."""
-        if not self.event:
-            raise RuntimeError("Compile must be ran before running any iterations")
-        out = self.event(**kwargs)
+        out = self._launch_events(**kwargs)
         self._iteration += 1
         return out
 
+    def _launch_events(self, **kwargs):
+        if not self.event:
+            raise RuntimeError("Compile must be ran before running any iterations")
+        self._plus_out = self.event(**kwargs)
+        return self._plus_out
+
     def _iteration_content(self):
         """vflowplus.py:222-242"""
+        self.run_event()
+        return self._iteration_epilogue()
+
+    def _iteration_epilogue(self):
         st = self._ensure_plus_state()
         lib = _lib.load()
-        ress, ress2, arr_res2 = self.run_event()
+        ress, ress2, arr_res2 = self._plus_out
         slot = self._result_slot()
         _lib.check(
             lib.vfp_iteration_epilogue(
