@@ -173,6 +173,15 @@ def run_reference_arm(args, wl):
 # ----------------------------------------------------------------------------
 # GPU arm
 # ----------------------------------------------------------------------------
+def _profiled_traffic(workload):
+    """DRAM bytes per event-kernel launch from the committed ncu --set full capture, or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            return json.load(f).get(workload)
+    except Exception:
+        return None
+
+
 def make_instance(wl, world):
     import vegasflow_b200 as vf
 
@@ -247,29 +256,32 @@ def main():
         torch.cuda.synchronize()
         extra += 1
 
-    # ---- timed region: exactly K steps, device-timed, max over ranks
+    # ---- timed region: exactly K steps of the product path, device-timed, max over ranks.
+    # Single rank: ONE vf_run_iterations call enqueues all K iterations (2 launches each).
+    # Multi rank: per iteration vf_run_event, the NCCL all-reduce, vf_iteration_epilogue.
     sampler = ClockSampler(torch.cuda.current_device())
     ev0 = torch.cuda.Event(enable_timing=True)
     ev1 = torch.cuda.Event(enable_timing=True)
-    kern_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-               for _ in range(K)]
     events_done = 0
+    batched = inst._fused_single_rank()
     barrier()
     lib.vf_launch_count(1)
+    lib.vf_kernel_timing(1)  # CUDA events around every event-kernel launch, same stream
     sampler.start()
     ev0.record()
-    for k in range(K):
-        # K1 (+ block reduction) bracketed on the launching stream for the roofline
-        events_done += inst.n_events
-        kern_ev[k][0].record()
-        out = inst._launch_events()
-        kern_ev[k][1].record()
-        inst._allreduce(out)
-        inst._iteration += 1
-        inst._iteration_epilogue()
+    if batched:
+        events_done = inst.n_events * K
+        inst._run_fused_iterations(K)
+    else:
+        for k in range(K):
+            events_done += inst.n_events
+            inst._run_iteration()
     ev1.record()
     barrier()
     launches = int(lib.vf_launch_count(0))
+    kt, kn = ctypes.c_double(0.0), ctypes.c_int(0)
+    _lib.check(lib.vf_kernel_time_ms(ctypes.byref(kt), ctypes.byref(kn)))
+    lib.vf_kernel_timing(0)
     ms = ev0.elapsed_time(ev1)
     # keep the same loop running ~1 s more so the clock sampler sees the kernel under load
     if sampler.nv is not None and ms < 1000.0:
@@ -284,7 +296,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    kern_ms = sum(a.elapsed_time(b) for a, b in kern_ev) / K
+    kern_ms = kt.value / max(kn.value, 1)
     value = events_done / (ms * 1e-3)
 
     # ---- e2e: public API, one D2H read of (res, sigma) per step like the reference's logging
@@ -331,12 +343,14 @@ def main():
             },
             "roofline": {
                 "bound": "fp64", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
-                "frac": achieved / peak.value, "traffic": None,
+                "frac": achieved / peak.value, "traffic": _profiled_traffic(args.workload),
                 "peak_source": "DFMA-chain probe run in this process (MEASURED_PEAKS.json has no "
                                "fp64 entry)",
                 "peak_nominal": FP64_NOMINAL_TFLOPS, "frac_of_nominal": achieved / FP64_NOMINAL_TFLOPS,
-                "flops_per_event": f_alg, "kernel": "event_kernel (+ finalize_kernel)",
-                "kernel_ms": kern_ms, "kernel_share_of_step": kern_ms / (ms / K),
+                "flops_per_event": f_alg,
+                "kernel": "plus_event_kernel" if plus else "event_kernel",
+                "kernel_ms": kern_ms, "kernel_launches_timed": kn.value,
+                "kernel_share_of_step": kern_ms / (ms / K),
             },
             "clocks": clocks,
             "e2e": {"value": e2e_events / e2e_s, "unit": UNIT,

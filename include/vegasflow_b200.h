@@ -114,6 +114,24 @@ int vf_iteration_epilogue(int n_dim, int64_t n_events, int train, const double* 
                           double* result /*[dev] [2]*/, void* stream);
 
 /*
+ * Whole single-device integration loop: n_iter iterations of (fused event kernel over all
+ * n_events, block reduction + sigma + grid refinement), enqueued back to back with no host
+ * synchronisation.  Replaces the iteration loop of run_integration (monte_carlo.py:679-685)
+ * over VegasFlow._iteration_content (vflow.py:432-442) / PlainFlow._run_iteration
+ * (plain.py:37-43) together with run_event + _accumulate (monte_carlo.py:420-480, 72-92).
+ * Iteration k uses Philox stream `first_iteration + k` and xjac = 1/n_events.
+ * results[k] = (res_k, sigma_k); packed = [hist n_dim*50 | sum wf | sum (wf)^2] of the last
+ * iteration; divisions is refined in place when train != 0.  The inverse-variance
+ * combination (monte_carlo.py:713-732) stays with the caller.
+ */
+int vf_run_iterations(int mode, int integrand, int n_dim, int64_t n_events, uint64_t seed,
+                      uint32_t first_iteration, int n_iter, int train,
+                      double* divisions /*[dev] in/out, NULL for PLAIN*/,
+                      const double* xmin /*[host]*/, const double* xdelta /*[host]*/,
+                      double* packed /*[dev] [n_dim*50+2]*/, double* results /*[dev] [n_iter][2]*/,
+                      void* workspace /*[dev]*/, size_t workspace_bytes, void* stream);
+
+/*
  * Parity entry: the same device code as vf_run_event, but fed external
  * uniforms at the reference's own RNG/algorithm seam
  * (_digest_random_generation, monte_carlo.py:268) and writing the per-event
@@ -199,6 +217,11 @@ int vfp_iteration_epilogue(int64_t n_cubes, const double* ress /*[dev]*/,
 /* Dependent-free DFMA chains on every SM; returns achieved fp64 TFLOP/s in *tflops
  * (device-timed with CUDA events, synchronous). */
 int vf_fp64_peak_probe(int iters, double* tflops /*[host]*/);
+/* Bracket every event-kernel launch of the calling thread with CUDA events on its launching
+ * stream (enable != 0 starts a fresh measurement, 0 stops); vf_kernel_time_ms synchronises on
+ * the recorded events and returns their summed duration and count. */
+int vf_kernel_timing(int enable);
+int vf_kernel_time_ms(double* total_ms /*[host]*/, int* launches /*[host]*/);
 /* Number of SMs of the current device. */
 int vf_sm_count(void);
 /* Kernels launched by this library on the calling thread since the last reset. */

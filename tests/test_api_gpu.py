@@ -323,3 +323,41 @@ def test_utils_consume_array_into_indices_gpu():
     for val, i in zip(input_array, indices):
         check_result[i] += val
     np.testing.assert_allclose(check_result, result)
+
+
+def test_batched_and_verbose_paths_agree():
+    """run_integration with verbose=False enqueues all iterations through one
+    vf_run_iterations call; verbose=True goes iteration by iteration.  Same seed, same events."""
+    out = []
+    for verbose in (False, True):
+        inst = VegasFlow(4, 100000, verbose=verbose)
+        inst.set_seed(99)
+        inst.compile(vf.integrands.symgauss)
+        out.append(inst.run_integration(4, log_time=False))
+        assert len(inst.history) == 4
+    assert abs(out[0][0] - out[1][0]) <= 1e-9 * abs(out[0][0])
+    assert abs(out[0][1] - out[1][1]) <= 1e-7 * out[0][1]
+
+
+def test_two_gpu_sharding_matches_single_gpu(tmp_path):
+    """torchrun with 2 ranks over NCCL: same seed -> same integral as one rank."""
+    import os
+    import subprocess
+    import sys
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = os.path.join(root, "tests", "dist_check.py")
+    out = tmp_path / "dist.json"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29611", script, str(out)]
+    subprocess.run(cmd, check=True, timeout=600, cwd=root)
+    data = json.load(open(out))
+    inst = VegasFlow(4, 400000, verbose=False)
+    inst.set_seed(2718)
+    inst.compile(vf.integrands.symgauss)
+    res, err = inst.run_integration(4)
+    assert abs(res - data["res"]) <= 1e-9 * abs(res)
+    assert abs(err - data["err"]) <= 1e-7 * err
+    np.testing.assert_allclose(inst.divisions.cpu().numpy(), np.array(data["grid"]), atol=1e-11)

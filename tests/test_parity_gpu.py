@@ -391,3 +391,64 @@ def test_fp64_probe_reports_sane_peak(lib):
     out = ctypes.c_double(0.0)
     _lib.check(lib.vf_fp64_peak_probe(2000, ctypes.byref(out)))
     assert 10.0 < out.value < 60.0, out.value  # B200 nominal 37.2 TFLOP/s
+
+
+def test_run_iterations_matches_per_call_path(lib):
+    """vf_run_iterations (whole loop, one call) == vf_run_event + vf_iteration_epilogue per
+    iteration: identical Philox streams, fixed-order scalar reductions."""
+    d, n, seed, iters = 4, 150000, 31, 4
+    for mode, iid, train in ((1, 0, 1), (1, 1, 0), (0, 0, 0)):
+        grid_a = to_dev(R.initial_divisions(d))
+        grid_b = to_dev(R.initial_divisions(d))
+        ws = torch.empty(lib.vf_workspace_bytes(d) // 8, dtype=torch.float64, device=dev())
+        packed = torch.zeros(d * 50 + 2, dtype=torch.float64, device=dev())
+        results = torch.zeros((iters, 2), dtype=torch.float64, device=dev())
+        _lib.check(lib.vf_run_iterations(mode, iid, d, n, seed, 5, iters, train, _lib.ptr(grid_a),
+                                         None, None, _lib.ptr(packed), _lib.ptr(results),
+                                         _lib.ptr(ws), ws.numel() * 8, _lib.stream_ptr()))
+        ref = torch.zeros((iters, 2), dtype=torch.float64, device=dev())
+        packed_b = torch.zeros_like(packed)
+        for it in range(iters):
+            _lib.check(lib.vf_run_event(mode, iid, d, 0, n, 1.0 / n, seed, 5 + it, train,
+                                        _lib.ptr(grid_b), None, None, _lib.ptr(packed_b[d * 50:]),
+                                        _lib.ptr(packed_b), 0, _lib.ptr(ws), ws.numel() * 8,
+                                        _lib.stream_ptr()))
+            _lib.check(lib.vf_iteration_epilogue(d, n, train, _lib.ptr(packed_b[d * 50:]),
+                                                 _lib.ptr(packed_b), _lib.ptr(grid_b),
+                                                 _lib.ptr(ref[it]), _lib.stream_ptr()))
+        torch.cuda.synchronize()
+        a, b = results.cpu().numpy(), ref.cpu().numpy()
+        np.testing.assert_allclose(a, b, rtol=1e-9)
+        assert a[0, 0] == b[0, 0]  # first iteration: same grid, fixed-order sums -> bitwise
+        np.testing.assert_allclose(grid_a.cpu().numpy(), grid_b.cpu().numpy(), rtol=0, atol=1e-12)
+        if train:
+            assert not np.array_equal(grid_a.cpu().numpy(), R.initial_divisions(d))
+        # against the C oracle on the same stream, iteration by iteration
+        if mode == 1:
+            grid = R.initial_divisions(d)
+            name = "symgauss" if iid == 0 else "product"
+            for it in range(iters):
+                s1, s2, hist = co.run_event(co.MODE_VEGAS, name, d, 0, n, 1.0 / n, seed, 5 + it,
+                                            True, grid)
+                assert abs(a[it, 0] - s1) <= 1e-9 * abs(s1)
+                assert abs(a[it, 1] - R.vegas_sigma(s1, s2, n)) <= 1e-7 * a[it, 1]
+                if train:
+                    grid = co.refine_grid(hist, grid)
+
+
+def test_kernel_timing_hook(lib):
+    import ctypes
+
+    d, n = 8, 2000000
+    grid = to_dev(R.initial_divisions(d))
+    ws = torch.empty(lib.vf_workspace_bytes(d) // 8, dtype=torch.float64, device=dev())
+    packed = torch.zeros(d * 50 + 2, dtype=torch.float64, device=dev())
+    results = torch.zeros((3, 2), dtype=torch.float64, device=dev())
+    lib.vf_kernel_timing(1)
+    _lib.check(lib.vf_run_iterations(1, 1, d, n, 1, 0, 3, 1, _lib.ptr(grid), None, None,
+                                     _lib.ptr(packed), _lib.ptr(results), _lib.ptr(ws),
+                                     ws.numel() * 8, _lib.stream_ptr()))
+    tot, cnt = ctypes.c_double(0.0), ctypes.c_int(0)
+    _lib.check(lib.vf_kernel_time_ms(ctypes.byref(tot), ctypes.byref(cnt)))
+    lib.vf_kernel_timing(0)
+    assert cnt.value == 3 and 0.0 < tot.value < 50.0

@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <vector>
 
 #include "vf_aux.cuh"
 #include "vf_event.cuh"
@@ -23,6 +24,31 @@ int cuda_fail(cudaError_t e, const char* what) {
     return VF_ERR_CUDA;
 }
 void count_launch(int n) { g_launches += n; }
+
+// Event-kernel timing hook: when enabled every event-kernel launch is bracketed by a pair of
+// CUDA events on the launching stream; vf_kernel_time_ms sums the elapsed times.
+struct TimingState {
+    bool on = false;
+    std::vector<cudaEvent_t> ev;  // start/stop pairs
+    size_t used = 0;
+};
+static thread_local TimingState g_timing;
+void timing_begin(cudaStream_t stream) {
+    if (!g_timing.on) return;
+    if (g_timing.used + 2 > g_timing.ev.size()) {
+        for (int k = 0; k < 2; ++k) {
+            cudaEvent_t e;
+            if (cudaEventCreate(&e) != cudaSuccess) return;
+            g_timing.ev.push_back(e);
+        }
+    }
+    cudaEventRecord(g_timing.ev[g_timing.used], stream);
+}
+void timing_end(cudaStream_t stream) {
+    if (!g_timing.on || g_timing.used + 2 > g_timing.ev.size()) return;
+    cudaEventRecord(g_timing.ev[g_timing.used + 1], stream);
+    g_timing.used += 2;
+}
 
 int sm_count() {
     static int cached[64] = {0};
@@ -190,6 +216,57 @@ int vf_run_event(int mode, int integrand, int n_dim, uint64_t ev_begin, int64_t 
     if (rc) return rc;
     return launch_finalize((const double*)workspace, nblocks, n_dim, with_hist, out_sums, out_hist,
                            accumulate, L.stream);
+}
+
+int vf_run_iterations(int mode, int integrand, int n_dim, int64_t n_events, uint64_t seed,
+                      uint32_t first_iteration, int n_iter, int train, double* divisions,
+                      const double* xmin, const double* xdelta, double* packed, double* results,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+    int rc = check_common(n_dim, n_events);
+    if (rc) return rc;
+    if (mode != VF_MODE_PLAIN && mode != VF_MODE_VEGAS) {
+        set_error("unknown mode %d", mode);
+        return VF_ERR_INVALID;
+    }
+    if (n_iter < 0 || n_events < 2 || !packed || !results || !workspace ||
+        (mode == VF_MODE_VEGAS && !divisions)) {
+        set_error("vf_run_iterations: bad arguments");
+        return VF_ERR_INVALID;
+    }
+    if (workspace_bytes < workspace_need(n_dim)) {
+        set_error("workspace too small: %zu < %zu", workspace_bytes, workspace_need(n_dim));
+        return VF_ERR_WORKSPACE;
+    }
+    const bool with_hist = mode == VF_MODE_VEGAS && train;
+    EventLaunch L;
+    L.mode = mode;
+    L.n_dim = n_dim;
+    L.stream = (cudaStream_t)stream;
+    int nblocks = 0;
+    L.nblocks_out = &nblocks;
+    rc = make_limits(n_dim, xmin, xdelta, &L.k.lim);
+    if (rc) return rc;
+    fill_consts(integrand, n_dim, &L.k.ic);
+    L.k.divisions = divisions;
+    L.k.partials = (double*)workspace;
+    L.k.ev_begin = 0;
+    L.k.ev_end = (uint64_t)n_events;
+    L.k.xjac = 1.0 / (double)n_events;  // monte_carlo.py:224-227
+    L.k.pk = make_philox_keys(seed);
+    L.k.train = train;
+    double* out_hist = packed;
+    double* out_sums = packed + (size_t)n_dim * kBins;
+    for (int it = 0; it < n_iter; ++it) {
+        L.k.iteration = first_iteration + (uint32_t)it;
+        rc = dispatch_integrand(integrand,
+                                [&](auto tag) { return launch_event<decltype(tag)>(L); });
+        if (rc) return rc;
+        rc = launch_finalize_epilogue((const double*)workspace, nblocks, n_dim, with_hist, n_events,
+                                      train, out_sums, out_hist, divisions, results + 2 * it,
+                                      L.stream);
+        if (rc) return rc;
+    }
+    return VF_OK;
 }
 
 int vf_refine_grid(int n_dim, const double* hist, double* divisions, void* stream) {
@@ -367,6 +444,29 @@ int vf_fp64_peak_probe(int iters, double* tflops) {
 }
 
 int vf_sm_count(void) { return sm_count(); }
+
+int vf_kernel_timing(int enable) {
+    g_timing.on = enable != 0;
+    g_timing.used = 0;
+    return VF_OK;
+}
+
+int vf_kernel_time_ms(double* total_ms, int* launches) {
+    if (!total_ms || !launches) {
+        set_error("vf_kernel_time_ms: null pointer");
+        return VF_ERR_INVALID;
+    }
+    double tot = 0.0;
+    for (size_t k = 0; k + 1 < g_timing.used; k += 2) {
+        VF_CUDA_CHECK(cudaEventSynchronize(g_timing.ev[k + 1]));
+        float ms = 0.f;
+        VF_CUDA_CHECK(cudaEventElapsedTime(&ms, g_timing.ev[k], g_timing.ev[k + 1]));
+        tot += ms;
+    }
+    *total_ms = tot;
+    *launches = (int)(g_timing.used / 2);
+    return VF_OK;
+}
 
 int64_t vf_launch_count(int reset) {
     const int64_t v = g_launches;

@@ -13,23 +13,34 @@ __host__ __device__ inline int64_t imin64(int64_t a, int64_t b) { return a < b ?
 // Block j < n_dim reduces the 50 bins of dimension j; block n_dim the scalars.
 // Replaces _accumulate (monte_carlo.py:72-92) for the blocks of one launch.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) finalize_kernel(const double* __restrict__ partials,
-                                                       int nblocks, int n_dim, int with_hist,
-                                                       double* out_sums, double* out_hist,
-                                                       int accumulate) {
-    __shared__ double part[4][64];
+constexpr int kFinSlicesMR = 16;
+__global__ void __launch_bounds__(64 * kFinSlicesMR) finalize_kernel(
+    const double* __restrict__ partials, int nblocks, int n_dim, int with_hist, double* out_sums,
+    double* out_hist, int accumulate) {
+    __shared__ double part[kFinSlicesMR][64];
     const size_t stride = partial_stride(n_dim);
     const int col = threadIdx.x & 63, slice = threadIdx.x >> 6;
-    const bool scalars = (int)blockIdx.x == n_dim;
+    const bool scalars = (int)blockIdx.x == (with_hist ? n_dim : 0);
     const int ncols = scalars ? 2 : kBins;
     const size_t base = scalars ? 0 : 2 + (size_t)blockIdx.x * kBins;
-    double t = 0.0;
-    if (col < ncols)
-        for (int b = slice; b < nblocks; b += 4) t += partials[(size_t)b * stride + base + col];
-    part[slice][col] = t;
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+    if (col < ncols) {
+        const double* p = partials + base + col;
+        int b = slice;
+        for (; b + 3 * kFinSlicesMR < nblocks; b += 4 * kFinSlicesMR) {
+            t0 += p[(size_t)b * stride];
+            t1 += p[(size_t)(b + kFinSlicesMR) * stride];
+            t2 += p[(size_t)(b + 2 * kFinSlicesMR) * stride];
+            t3 += p[(size_t)(b + 3 * kFinSlicesMR) * stride];
+        }
+        for (; b < nblocks; b += kFinSlicesMR) t0 += p[(size_t)b * stride];
+    }
+    part[slice][col] = (t0 + t1) + (t2 + t3);
     __syncthreads();
     if (slice == 0 && col < ncols) {
-        const double tot = ((part[0][col] + part[1][col]) + part[2][col]) + part[3][col];
+        double tot = 0.0;
+#pragma unroll
+        for (int k = 0; k < kFinSlicesMR; ++k) tot += part[k][col];
         double* out = scalars ? out_sums + col : out_hist + (size_t)blockIdx.x * kBins + col;
         *out = accumulate ? *out + tot : tot;
     }
@@ -37,35 +48,13 @@ __global__ void __launch_bounds__(256) finalize_kernel(const double* __restrict_
 
 int launch_finalize(const double* partials, int nblocks, int n_dim, bool with_hist,
                     double* out_sums, double* out_hist, int accumulate, cudaStream_t stream) {
-    // blocks [0, n_dim) only when a histogram is wanted; the scalar block always runs
-    if (with_hist) {
-        finalize_kernel<<<n_dim + 1, 256, 0, stream>>>(partials, nblocks, n_dim, 1, out_sums,
-                                                      out_hist, accumulate);
-    } else {
-        // launch only the scalar block: shift blockIdx by giving n_dim blocks zero work
-        finalize_scalars_kernel<<<1, 256, 0, stream>>>(partials, nblocks, n_dim, out_sums,
-                                                      accumulate);
-    }
+    // blocks [0, n_dim) reduce the histogram rows (only when one is wanted), the last block
+    // the two scalars
+    finalize_kernel<<<with_hist ? n_dim + 1 : 1, 64 * kFinSlicesMR, 0, stream>>>(
+        partials, nblocks, n_dim, with_hist ? 1 : 0, out_sums, out_hist, accumulate);
     count_launch();
     VF_CUDA_CHECK(cudaGetLastError());
     return VF_OK;
-}
-
-__global__ void __launch_bounds__(256) finalize_scalars_kernel(const double* __restrict__ partials,
-                                                               int nblocks, int n_dim,
-                                                               double* out_sums, int accumulate) {
-    __shared__ double part[4][64];
-    const size_t stride = partial_stride(n_dim);
-    const int col = threadIdx.x & 63, slice = threadIdx.x >> 6;
-    double t = 0.0;
-    if (col < 2)
-        for (int b = slice; b < nblocks; b += 4) t += partials[(size_t)b * stride + col];
-    part[slice][col] = t;
-    __syncthreads();
-    if (slice == 0 && col < 2) {
-        const double tot = ((part[0][col] + part[1][col]) + part[2][col]) + part[3][col];
-        out_sums[col] = accumulate ? out_sums[col] + tot : tot;
-    }
 }
 
 // ---------------------------------------------------------------------------
@@ -108,22 +97,37 @@ __device__ void refine_dimension(const double* __restrict__ t_res_sq, double* su
         for (int k = 0; k < kBins; ++k) s = __dadd_rn(s, wei[k]);
         const double ave = __ddiv_rn(s, (double)kBins);  // :166
         s_ave = ave;
-        // serial scan :195-205 (state: bin_weight, n_bin, cur, prev)
+        // serial scan :195-205 (state: bin_weight, n_bin, cur, prev).  The reference advances
+        // n while bin_weight < ave and then emits one boundary; here the same sequence of
+        // additions/subtractions/comparisons is driven by n (static, fully unrolled, operands
+        // at fixed shared-memory addresses) with the emits in an inner loop -- identical
+        // floating-point operations in the identical order, without dynamic indexing on the
+        // critical path.
         double bw = 0.0, cur = 0.0, prev = 0.0;
-        int n = -1;
-        for (int k = 1; k < kBins; ++k) {
-            while (bw < ave) {  // :170-190
-                n += 1;
-                if (n > kBins - 1) { n = kBins - 1; break; }  // guard
-                bw = __dadd_rn(bw, wei[n]);
-                prev = cur;
-                cur = sub[n + 1];
+        int k = 1;
+#pragma unroll
+        for (int n = 0; n < kBins; ++n) {
+            if (k < kBins) {
+                bw = __dadd_rn(bw, wei[n]);  // :187
+                prev = cur;                  // :188
+                cur = sub[n + 1];            // :189
+                while (k < kBins && !(bw < ave)) {
+                    bw = __dsub_rn(bw, ave);  // :205
+                    b_cur[k] = cur;
+                    b_prev[k] = prev;
+                    b_bw[k] = bw;
+                    b_n[k] = n;
+                    ++k;
+                }
             }
-            bw = __dsub_rn(bw, ave);  // :205
+        }
+        // guard: if round-off left boundaries unassigned, close them on the last bin
+        for (; k < kBins; ++k) {
+            bw = __dsub_rn(bw, ave);
             b_cur[k] = cur;
             b_prev[k] = prev;
             b_bw[k] = bw;
-            b_n[k] = n;
+            b_n[k] = kBins - 1;
         }
     }
     __syncthreads();
@@ -166,6 +170,75 @@ __global__ void __launch_bounds__(64) epilogue_kernel(int n_dim, double n_events
     if (train)
         refine_dimension(hist + (size_t)blockIdx.x * kBins,
                          divisions + (size_t)blockIdx.x * kEdges);
+}
+
+// Single-rank fusion of finalize_kernel and epilogue_kernel: block j < n_dim reduces the
+// per-block partial histograms of dimension j (fixed order), stores the row, and refines that
+// dimension in place; block n_dim reduces the two scalars and writes (res, sigma).
+// 1024 threads = 64 columns x 16 slices so the ~300 partial records are read with high
+// memory-level parallelism (4 independent accumulators per thread).
+constexpr int kFinSlices = 16;
+__global__ void __launch_bounds__(64 * kFinSlices) finalize_epilogue_kernel(
+    const double* __restrict__ partials, int nblocks, int n_dim, int with_hist, double n_events,
+    int train, double* out_sums, double* out_hist, double* divisions, double* result) {
+    __shared__ double part[kFinSlices][64];
+    __shared__ double row[kBins];
+    const size_t stride = partial_stride(n_dim);
+    const int col = threadIdx.x & 63, slice = threadIdx.x >> 6;
+    // without a histogram the grid is the single scalar block
+    const bool scalars = (int)blockIdx.x == (with_hist ? n_dim : 0);
+    const int ncols = scalars ? 2 : kBins;
+    const size_t base = scalars ? 0 : 2 + (size_t)blockIdx.x * kBins;
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+    if (col < ncols) {
+        const double* p = partials + base + col;
+        int b = slice;
+        for (; b + 3 * kFinSlices < nblocks; b += 4 * kFinSlices) {
+            t0 += p[(size_t)b * stride];
+            t1 += p[(size_t)(b + kFinSlices) * stride];
+            t2 += p[(size_t)(b + 2 * kFinSlices) * stride];
+            t3 += p[(size_t)(b + 3 * kFinSlices) * stride];
+        }
+        for (; b < nblocks; b += kFinSlices) t0 += p[(size_t)b * stride];
+    }
+    part[slice][col] = (t0 + t1) + (t2 + t3);
+    __syncthreads();
+    if (slice == 0 && col < ncols) {
+        double tot = 0.0;
+#pragma unroll
+        for (int k = 0; k < kFinSlices; ++k) tot += part[k][col];
+        if (scalars) {
+            out_sums[col] = tot;
+            part[0][col] = tot;
+        } else {
+            out_hist[(size_t)blockIdx.x * kBins + col] = tot;
+            row[col] = tot;
+        }
+    }
+    __syncthreads();
+    if (scalars) {
+        if (threadIdx.x == 0) {
+            const double res = part[0][0], res2 = part[0][1];
+            const double err_tmp2 = __ddiv_rn(
+                __dsub_rn(__dmul_rn(n_events, res2), __dmul_rn(res, res)), n_events - 1.0);
+            result[0] = res;
+            result[1] = sqrt(fmax(err_tmp2, 0.0));
+        }
+        return;
+    }
+    if (train) refine_dimension(row, divisions + (size_t)blockIdx.x * kEdges);
+}
+
+int launch_finalize_epilogue(const double* partials, int nblocks, int n_dim, bool with_hist,
+                             int64_t n_events, int train, double* out_sums, double* out_hist,
+                             double* divisions, double* result, cudaStream_t stream) {
+    const int blocks = with_hist ? n_dim + 1 : 1;
+    finalize_epilogue_kernel<<<blocks, 64 * kFinSlices, 0, stream>>>(partials, nblocks, n_dim, with_hist ? 1 : 0,
+                                                        (double)n_events, train, out_sums, out_hist,
+                                                        divisions, result);
+    count_launch();
+    VF_CUDA_CHECK(cudaGetLastError());
+    return VF_OK;
 }
 
 int launch_epilogue(int n_dim, int64_t n_events, int train, const double* sums, const double* hist,

@@ -4,11 +4,11 @@
 
 namespace vf {
 
-__global__ void finalize_scalars_kernel(const double* __restrict__ partials, int nblocks, int n_dim,
-                                        double* out_sums, int accumulate);
-
 int launch_finalize(const double* partials, int nblocks, int n_dim, bool with_hist,
                     double* out_sums, double* out_hist, int accumulate, cudaStream_t stream);
+int launch_finalize_epilogue(const double* partials, int nblocks, int n_dim, bool with_hist,
+                             int64_t n_events, int train, double* out_sums, double* out_hist,
+                             double* divisions, double* result, cudaStream_t stream);
 int launch_refine(int n_dim, const double* hist, double* divisions, cudaStream_t stream);
 int launch_epilogue(int n_dim, int64_t n_events, int train, const double* sums, const double* hist,
                     double* divisions, double* result, cudaStream_t stream);

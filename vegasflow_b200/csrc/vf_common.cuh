@@ -22,6 +22,9 @@ void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
 void count_launch(int n = 1);
 int sm_count();
+// optional CUDA-event bracket around the event kernels (vf_kernel_timing)
+void timing_begin(cudaStream_t stream);
+void timing_end(cudaStream_t stream);
 
 #define VF_CUDA_CHECK(expr)                                   \
     do {                                                      \

@@ -429,7 +429,9 @@ int launch_event_dim(const EventLaunch& L) {
     }
     const int64_t n = (int64_t)(L.k.ev_end - L.k.ev_begin);
     const int blocks = grid_blocks_for(n, C::kThreads, min_blocks<I, NDIM>());
+    timing_begin(L.stream);
     kern<<<blocks, C::kThreads, smem, L.stream>>>(L.k);
+    timing_end(L.stream);
     count_launch();
     *L.nblocks_out = blocks;
     VF_CUDA_CHECK(cudaGetLastError());
@@ -461,7 +463,9 @@ int launch_plus_dim(const PlusLaunch& L) {
     VF_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)C::kSmemBytes));
     const int blocks = grid_blocks_for(L.k.n_events, C::kThreads, min_blocks<I, NDIM>());
+    timing_begin(L.stream);
     kern<<<blocks, C::kThreads, C::kSmemBytes, L.stream>>>(L.k);
+    timing_end(L.stream);
     count_launch();
     *L.nblocks_out = blocks;
     VF_CUDA_CHECK(cudaGetLastError());

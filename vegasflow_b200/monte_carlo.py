@@ -69,6 +69,8 @@ class MonteCarloFlow(ABC):
 
     _CAN_RUN_VECTORIAL = False
     _MODE = _lib.MODE_PLAIN
+    # True when whole iterations can be enqueued by vf_run_iterations (single rank, fused)
+    _BATCHABLE = False
 
     def __init__(
         self,
@@ -145,15 +147,43 @@ class MonteCarloFlow(ABC):
         self._results = torch.zeros((64, 2), dtype=DTYPE, device=self._device)
         self._results_used = 0
 
-    def _result_slot(self):
-        """Device row that receives (res, sigma) of the next iteration."""
-        if self._results_used >= self._results.shape[0]:
-            grown = torch.zeros((2 * self._results.shape[0], 2), dtype=DTYPE, device=self._device)
+    def _result_rows(self, n):
+        """`n` consecutive device rows that receive (res, sigma) of the next iterations."""
+        if self._results_used + n > self._results.shape[0]:
+            size = max(2 * self._results.shape[0], self._results_used + n)
+            grown = torch.zeros((size, 2), dtype=DTYPE, device=self._device)
             grown[: self._results.shape[0]] = self._results
             self._results = grown
-        slot = self._results[self._results_used]
-        self._results_used += 1
-        return slot
+        rows = self._results[self._results_used : self._results_used + n]
+        self._results_used += n
+        return rows
+
+    def _result_slot(self):
+        """Device row that receives (res, sigma) of the next iteration."""
+        return self._result_rows(1)[0]
+
+    def _fused_single_rank(self):
+        return (self._BATCHABLE and self._builtin is not None and not self._vectorial
+                and parallel.world()[1] == 1)
+
+    def _run_fused_iterations(self, n_iter):
+        """Enqueue `n_iter` whole iterations with ONE C-ABI call (vf_run_iterations): per
+        iteration the fused event kernel and the reduce+sigma+refine kernel, no host sync.
+        Returns the device rows [(res, sigma)] * n_iter."""
+        self._ensure_device()
+        lib = _lib.load()
+        rows = self._result_rows(n_iter)
+        _lib.check(
+            lib.vf_run_iterations(
+                self._MODE, self._builtin.integrand_id(), self.n_dim, self.n_events, self._seed,
+                self._iteration, n_iter, int(bool(getattr(self, "train", False))),
+                _lib.ptr(self._grid_tensor()), self._xmin_c, self._xdelta_c,
+                _lib.ptr(self._packed), _lib.ptr(rows), _lib.ptr(self._workspace),
+                self._workspace.numel() * 8, _lib.stream_ptr(),
+            )
+        )
+        self._iteration += n_iter
+        return rows
 
     @property
     def _hist(self):
@@ -415,10 +445,18 @@ class MonteCarloFlow(ABC):
         """
         if histograms is not None:
             raise NotImplementedError("user histograms are out of scope of the B200 engine")
+        if not self.event:
+            raise RuntimeError("Compile must be ran before running any iterations")
         self._ensure_device()
         all_results = []
         first_slot = len(self._history)
-        for i in range(n_iter):
+        batched = self._fused_single_rank() and not self._verbose
+        if batched:
+            rows = self._run_fused_iterations(n_iter)
+            for k in range(n_iter):
+                all_results.append((rows[k, 0], rows[k, 1]))
+                self._history.append((rows[k, 0], rows[k, 1], None))
+        for i in range(0 if batched else n_iter):
             start = time.time() if log_time else None
             res, error = self._run_iteration()
             all_results.append((res, error))
@@ -436,7 +474,10 @@ class MonteCarloFlow(ABC):
             self._history.append((res, error, None))
 
         # One read-back for everything that is still on the device
-        host = [(self._to_host(r), self._to_host(e)) for r, e in all_results]
+        if batched:
+            host = [tuple(row) for row in rows.detach().cpu().tolist()]
+        else:
+            host = [(self._to_host(r), self._to_host(e)) for r, e in all_results]
         for k, (r, e) in enumerate(host):
             self._history[first_slot + k] = (r, e, None)
 

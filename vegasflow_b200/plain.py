@@ -15,6 +15,7 @@ class PlainFlow(MonteCarloFlow):
 
     _CAN_RUN_VECTORIAL = True
     _MODE = _lib.MODE_PLAIN
+    _BATCHABLE = True
 
     def __init__(self, *args, **kwargs):
         super().__init__(*args, **kwargs)
@@ -65,6 +66,9 @@ class PlainFlow(MonteCarloFlow):
 
     def _run_iteration(self):
         """plain.py:37-43"""
+        if self._fused_single_rank():
+            row = self._run_fused_iterations(1)[0]
+            return row[0], row[1]
         self.run_event()
         return self._iteration_epilogue()
 

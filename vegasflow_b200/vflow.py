@@ -44,6 +44,7 @@ class VegasFlow(MonteCarloFlow):
     """
 
     _MODE = _lib.MODE_VEGAS
+    _BATCHABLE = True
 
     def __init__(self, n_dim, n_events, train=True, main_dimension=0, **kwargs):
         super().__init__(n_dim, n_events, **kwargs)
@@ -208,6 +209,9 @@ class VegasFlow(MonteCarloFlow):
 
     def _iteration_content(self):
         """Steps to follow per iteration (vflow.py:432-442)"""
+        if self._fused_single_rank():
+            row = self._run_fused_iterations(1)[0]
+            return row[0], row[1]
         self.run_event()
         return self._iteration_epilogue()
 

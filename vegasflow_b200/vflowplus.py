@@ -33,6 +33,8 @@ def _n_strat_for(neval_eff, n_dim):
 class VegasFlowPlus(VegasFlow):
     """Implementation of the VEGAS+ algorithm (vflowplus.py:83-247)."""
 
+    _BATCHABLE = False  # the event count changes between iterations (adaptive)
+
     def __init__(self, n_dim, n_events, train=True, adaptive=False, events_limit=None, **kwargs):
         # vflowplus.py:90-100
         if events_limit is None:
