@@ -67,7 +67,9 @@ int vf_supported(int integrand, int n_dim);
 /* Algorithmic fp64 flops per event of the fused iteration. */
 double vf_flops_per_event(int mode, int integrand, int n_dim, int plus);
 
-/* Scratch (bytes) the event kernels need for per-block partial results. */
+/* Scratch (bytes) for per-block scalar records and the global histogram accumulator.
+ * The caller ZERO-INITIALISES the workspace once before its first use; the library leaves the
+ * accumulator zeroed after every reduction, so the same workspace is reused across calls. */
 size_t vf_workspace_bytes(int n_dim);
 
 /*
@@ -130,6 +132,31 @@ int vf_run_iterations(int mode, int integrand, int n_dim, int64_t n_events, uint
                       const double* xmin /*[host]*/, const double* xdelta /*[host]*/,
                       double* packed /*[dev] [n_dim*50+2]*/, double* results /*[dev] [n_iter][2]*/,
                       void* workspace /*[dev]*/, size_t workspace_bytes, void* stream);
+
+/*
+ * n_iter iterations of one rank of a multi-GPU run, each fused with its collective: the event
+ * kernel over this rank's events [ev_begin, ev_begin + n_events_local), then ONE kernel that reduces
+ * the block partials, exchanges the [n_dim*50+2] sums with all peers by P2P stores over
+ * NVLink (one-shot all-reduce on peer-mapped memory, flags with release/acquire at system
+ * scope), adds the `world` contributions in rank order, computes (res, sigma) and refines the
+ * grid -- every rank ends with bit-identical divisions.  Replaces the joblib device pool and
+ * host-side _accumulate of the reference (monte_carlo.py:143-157, 318-365, 454-480, 72-92).
+ * peer_buffers: [host] `world` device addresses of every rank's exchange buffer of
+ * vf_exchange_bytes(n_dim, world) bytes (zero-initialised, peer-mapped, e.g. torch symmetric
+ * memory); iteration k uses exchange sequence number first_seq + k: the sequence must start
+ * at 1 and advance by one per iteration, identically on every rank.  world <= 8.
+ * results[k] = (res_k, sigma_k).
+ */
+size_t vf_exchange_bytes(int n_dim, int world);
+int vf_run_iterations_sharded(int mode, int integrand, int n_dim, uint64_t ev_begin,
+                              int64_t n_events_local, int64_t n_events_total, uint64_t seed,
+                              uint32_t first_iteration, int n_iter, int train,
+                              double* divisions /*[dev]*/, const double* xmin /*[host]*/,
+                              const double* xdelta /*[host]*/, double* packed /*[dev] [n_dim*50+2]*/,
+                              double* results /*[dev] [n_iter][2]*/, void* workspace /*[dev]*/,
+                              size_t workspace_bytes, int rank, int world,
+                              const uint64_t* peer_buffers /*[host] [world]*/, uint64_t first_seq,
+                              void* stream);
 
 /*
  * Parity entry: the same device code as vf_run_event, but fed external
@@ -222,6 +249,8 @@ int vf_fp64_peak_probe(int iters, double* tflops /*[host]*/);
  * the recorded events and returns their summed duration and count. */
 int vf_kernel_timing(int enable);
 int vf_kernel_time_ms(double* total_ms /*[host]*/, int* launches /*[host]*/);
+/* Same for the reduce/exchange/refine kernels that follow each event kernel. */
+int vf_epilogue_time_ms(double* total_ms /*[host]*/, int* launches /*[host]*/);
 /* Number of SMs of the current device. */
 int vf_sm_count(void);
 /* Kernels launched by this library on the calling thread since the last reset. */

@@ -26,7 +26,8 @@ def main():
     assert torch.equal(g, inst.divisions), "ranks diverged"
     if dist.get_rank() == 0:
         with open(sys.argv[1], "w") as f:
-            json.dump({"res": res, "err": err, "grid": grid.tolist()}, f)
+            json.dump({"res": res, "err": err, "grid": grid.tolist(),
+                       "exchange": "p2p" if inst._exchange is not None else "nccl"}, f)
     dist.destroy_process_group()
 
 

@@ -349,15 +349,20 @@ def test_two_gpu_sharding_matches_single_gpu(tmp_path):
         pytest.skip("needs 2 GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     script = os.path.join(root, "tests", "dist_check.py")
-    out = tmp_path / "dist.json"
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-           "--master-addr", "127.0.0.1", "--master-port", "29611", script, str(out)]
-    subprocess.run(cmd, check=True, timeout=600, cwd=root)
-    data = json.load(open(out))
     inst = VegasFlow(4, 400000, verbose=False)
     inst.set_seed(2718)
     inst.compile(vf.integrands.symgauss)
     res, err = inst.run_integration(4)
-    assert abs(res - data["res"]) <= 1e-9 * abs(res)
-    assert abs(err - data["err"]) <= 1e-7 * err
-    np.testing.assert_allclose(inst.divisions.cpu().numpy(), np.array(data["grid"]), atol=1e-11)
+    grid = inst.divisions.cpu().numpy()
+    # both collectives: the fused NVLink peer-memory kernel and the NCCL all-reduce path
+    for k, exchange in enumerate(("p2p", "nccl")):
+        out = tmp_path / f"dist_{exchange}.json"
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+               "--master-addr", "127.0.0.1", "--master-port", str(29611 + k), script, str(out)]
+        env = dict(os.environ, VEGASFLOW_B200_EXCHANGE=exchange)
+        subprocess.run(cmd, check=True, timeout=600, cwd=root, env=env)
+        data = json.load(open(out))
+        assert data["exchange"] == exchange
+        assert abs(res - data["res"]) <= 1e-9 * abs(res)
+        assert abs(err - data["err"]) <= 1e-7 * err
+        np.testing.assert_allclose(grid, np.array(data["grid"]), atol=1e-11)

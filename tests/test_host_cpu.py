@@ -55,7 +55,7 @@ def test_abi_host_only_entry_points():
     assert lib.vf_flops_per_event(1, 0, 20, 0) == 329
     assert lib.vf_flops_per_event(1, 1, 8, 0) == 108
     assert lib.vf_flops_per_event(1, 0, 8, 1) == 146
-    assert lib.vf_workspace_bytes(8) >= 296 * (2 + 400) * 8
+    assert lib.vf_workspace_bytes(8) >= (296 * 2 + 400) * 8
     # argument validation happens before any CUDA call
     assert lib.vf_run_event(1, 0, 0, 0, 10, 1.0, 0, 0, 1, None, None, None, None, None, 0, None, 0,
                             None) == -1

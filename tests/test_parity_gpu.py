@@ -54,7 +54,7 @@ def gpu_digest(lib, mode, iid, rnds, grid, xjac, xmin=None, xdelta=None):
 def gpu_run_event(lib, mode, iid, d, ev_begin, n, xjac, seed, iteration, train, grid, xmin=None,
                   xdelta=None):
     packed = torch.zeros(d * 50 + 2, dtype=torch.float64, device=dev())
-    ws = torch.empty(lib.vf_workspace_bytes(d) // 8, dtype=torch.float64, device=dev())
+    ws = torch.zeros(lib.vf_workspace_bytes(d) // 8, dtype=torch.float64, device=dev())
     t_g = None if grid is None else to_dev(grid)
     xm, xd = _lib.host_doubles(xmin), _lib.host_doubles(xdelta)
     _lib.check(lib.vf_run_event(mode, iid, d, ev_begin, n, xjac, seed, iteration, int(train),
@@ -199,7 +199,7 @@ def test_accumulate_flag(lib):
     d, n = 4, 50000
     grid = to_dev(R.initial_divisions(d))
     packed = torch.zeros(d * 50 + 2, dtype=torch.float64, device=dev())
-    ws = torch.empty(lib.vf_workspace_bytes(d) // 8, dtype=torch.float64, device=dev())
+    ws = torch.zeros(lib.vf_workspace_bytes(d) // 8, dtype=torch.float64, device=dev())
     for k, acc in enumerate((0, 1, 1)):
         _lib.check(lib.vf_run_event(1, 0, d, k * n, n, 1.0 / (3 * n), 3, 0, 1, _lib.ptr(grid), None,
                                     None, _lib.ptr(packed[d * 50:]), _lib.ptr(packed), acc,
@@ -270,7 +270,7 @@ def test_sample_and_accumulate_unfused_pair(lib):
     np.testing.assert_array_equal(ind.cpu().numpy(), io)
     f = torch.prod(x, dim=1)
     packed = torch.zeros(d * 50 + 2, dtype=torch.float64, device=dev())
-    ws = torch.empty(lib.vf_workspace_bytes(d) // 8, dtype=torch.float64, device=dev())
+    ws = torch.zeros(lib.vf_workspace_bytes(d) // 8, dtype=torch.float64, device=dev())
     _lib.check(lib.vf_accumulate(d, n, _lib.ptr(w), _lib.ptr(f), _lib.ptr(ind), 1,
                                  _lib.ptr(packed[d * 50:]), _lib.ptr(packed), 0, _lib.ptr(ws),
                                  ws.numel() * 8, _lib.stream_ptr()))
@@ -292,7 +292,7 @@ def test_plus_kernel_against_golden(lib, golden):
     ress = torch.zeros(n_cubes, dtype=torch.float64, device=dev())
     ress2 = torch.zeros_like(ress)
     hist = torch.zeros(d * 50, dtype=torch.float64, device=dev())
-    ws = torch.empty(lib.vf_workspace_bytes(d) // 8, dtype=torch.float64, device=dev())
+    ws = torch.zeros(lib.vf_workspace_bytes(d) // 8, dtype=torch.float64, device=dev())
     x = torch.empty((n, d), dtype=torch.float64, device=dev())
     w = torch.empty(n, dtype=torch.float64, device=dev())
     ind = torch.empty((n, d), dtype=torch.int32, device=dev())
@@ -349,7 +349,7 @@ def test_plus_fused_philox_against_oracle(lib):
     ress = torch.zeros(n_cubes, dtype=torch.float64, device=dev())
     ress2 = torch.zeros_like(ress)
     hist = torch.zeros(d * 50, dtype=torch.float64, device=dev())
-    ws = torch.empty(lib.vf_workspace_bytes(d) // 8, dtype=torch.float64, device=dev())
+    ws = torch.zeros(lib.vf_workspace_bytes(d) // 8, dtype=torch.float64, device=dev())
     t_nev, t_off, t_g = to_dev(n_ev), to_dev(off), to_dev(grid)
     _lib.check(lib.vfp_run_event(0, d, n_strat, n_cubes, n, _lib.ptr(t_nev), _lib.ptr(t_off),
                                  1.0 / n_cubes, 99, 4, 1, _lib.ptr(t_g), None, None, _lib.ptr(ress),
@@ -366,14 +366,14 @@ def test_plus_fused_philox_against_oracle(lib):
 
 def test_abi_error_codes_on_device(lib):
     d = 4
-    ws = torch.empty(16, dtype=torch.float64, device=dev())
+    ws = torch.zeros(16, dtype=torch.float64, device=dev())
     packed = torch.zeros(d * 50 + 2, dtype=torch.float64, device=dev())
     grid = to_dev(R.initial_divisions(d))
     rc = lib.vf_run_event(1, 0, d, 0, 10, 1.0, 0, 0, 1, _lib.ptr(grid), None, None,
                           _lib.ptr(packed[d * 50:]), _lib.ptr(packed), 0, _lib.ptr(ws), 128,
                           _lib.stream_ptr())
     assert rc == -4 and "workspace" in _lib.last_error()
-    ws = torch.empty(lib.vf_workspace_bytes(9) // 8, dtype=torch.float64, device=dev())
+    ws = torch.zeros(lib.vf_workspace_bytes(9) // 8, dtype=torch.float64, device=dev())
     rc = lib.vf_run_event(1, 0, 9, 0, 10, 1.0, 0, 0, 0, _lib.ptr(grid), None, None,
                           _lib.ptr(packed), None, 0, _lib.ptr(ws), ws.numel() * 8,
                           _lib.stream_ptr())
@@ -400,7 +400,7 @@ def test_run_iterations_matches_per_call_path(lib):
     for mode, iid, train in ((1, 0, 1), (1, 1, 0), (0, 0, 0)):
         grid_a = to_dev(R.initial_divisions(d))
         grid_b = to_dev(R.initial_divisions(d))
-        ws = torch.empty(lib.vf_workspace_bytes(d) // 8, dtype=torch.float64, device=dev())
+        ws = torch.zeros(lib.vf_workspace_bytes(d) // 8, dtype=torch.float64, device=dev())
         packed = torch.zeros(d * 50 + 2, dtype=torch.float64, device=dev())
         results = torch.zeros((iters, 2), dtype=torch.float64, device=dev())
         _lib.check(lib.vf_run_iterations(mode, iid, d, n, seed, 5, iters, train, _lib.ptr(grid_a),
@@ -441,7 +441,7 @@ def test_kernel_timing_hook(lib):
 
     d, n = 8, 2000000
     grid = to_dev(R.initial_divisions(d))
-    ws = torch.empty(lib.vf_workspace_bytes(d) // 8, dtype=torch.float64, device=dev())
+    ws = torch.zeros(lib.vf_workspace_bytes(d) // 8, dtype=torch.float64, device=dev())
     packed = torch.zeros(d * 50 + 2, dtype=torch.float64, device=dev())
     results = torch.zeros((3, 2), dtype=torch.float64, device=dev())
     lib.vf_kernel_timing(1)

@@ -29,25 +29,27 @@ void count_launch(int n) { g_launches += n; }
 // CUDA events on the launching stream; vf_kernel_time_ms sums the elapsed times.
 struct TimingState {
     bool on = false;
-    std::vector<cudaEvent_t> ev;  // start/stop pairs
-    size_t used = 0;
+    std::vector<cudaEvent_t> ev[2];  // start/stop pairs; category 0 = event kernels, 1 = epilogues
+    size_t used[2] = {0, 0};
 };
 static thread_local TimingState g_timing;
-void timing_begin(cudaStream_t stream) {
+void timing_begin(cudaStream_t stream, int category) {
     if (!g_timing.on) return;
-    if (g_timing.used + 2 > g_timing.ev.size()) {
+    auto& ev = g_timing.ev[category];
+    size_t& used = g_timing.used[category];
+    if (used + 2 > ev.size()) {
         for (int k = 0; k < 2; ++k) {
             cudaEvent_t e;
             if (cudaEventCreate(&e) != cudaSuccess) return;
-            g_timing.ev.push_back(e);
+            ev.push_back(e);
         }
     }
-    cudaEventRecord(g_timing.ev[g_timing.used], stream);
+    cudaEventRecord(ev[used], stream);
 }
-void timing_end(cudaStream_t stream) {
-    if (!g_timing.on || g_timing.used + 2 > g_timing.ev.size()) return;
-    cudaEventRecord(g_timing.ev[g_timing.used + 1], stream);
-    g_timing.used += 2;
+void timing_end(cudaStream_t stream, int category) {
+    if (!g_timing.on || g_timing.used[category] + 2 > g_timing.ev[category].size()) return;
+    cudaEventRecord(g_timing.ev[category][g_timing.used[category] + 1], stream);
+    g_timing.used[category] += 2;
 }
 
 int sm_count() {
@@ -98,7 +100,7 @@ static void fill_consts(int integrand, int n_dim, IntegrandConsts* ic) {
 }
 
 static size_t workspace_need(int n_dim) {
-    return ((size_t)kMaxBlocks * partial_stride(n_dim) + 2) * sizeof(double);
+    return ws_doubles(n_dim) * sizeof(double);
 }
 
 static int check_common(int n_dim, int64_t n) {
@@ -214,7 +216,7 @@ int vf_run_event(int mode, int integrand, int n_dim, uint64_t ev_begin, int64_t 
     L.k.train = train;
     rc = dispatch_integrand(integrand, [&](auto tag) { return launch_event<decltype(tag)>(L); });
     if (rc) return rc;
-    return launch_finalize((const double*)workspace, nblocks, n_dim, with_hist, out_sums, out_hist,
+    return launch_finalize((double*)workspace, nblocks, n_dim, with_hist, out_sums, out_hist,
                            accumulate, L.stream);
 }
 
@@ -261,8 +263,71 @@ int vf_run_iterations(int mode, int integrand, int n_dim, int64_t n_events, uint
         rc = dispatch_integrand(integrand,
                                 [&](auto tag) { return launch_event<decltype(tag)>(L); });
         if (rc) return rc;
-        rc = launch_finalize_epilogue((const double*)workspace, nblocks, n_dim, with_hist, n_events,
+        rc = launch_finalize_epilogue((double*)workspace, nblocks, n_dim, with_hist, n_events,
                                       train, out_sums, out_hist, divisions, results + 2 * it,
+                                      L.stream);
+        if (rc) return rc;
+    }
+    return VF_OK;
+}
+
+size_t vf_exchange_bytes(int n_dim, int world) {
+    return (n_dim < 1 || world < 1) ? 0 : exchange_bytes(n_dim, world);
+}
+
+int vf_run_iterations_sharded(int mode, int integrand, int n_dim, uint64_t ev_begin,
+                              int64_t n_events_local, int64_t n_events_total, uint64_t seed,
+                              uint32_t first_iteration, int n_iter, int train, double* divisions,
+                              const double* xmin, const double* xdelta, double* packed,
+                              double* results, void* workspace, size_t workspace_bytes, int rank,
+                              int world, const uint64_t* peer_buffers, uint64_t first_seq,
+                              void* stream) {
+    double* result = results;
+    const uint64_t seq = first_seq;
+    int rc = check_common(n_dim, n_events_local);
+    if (rc) return rc;
+    if (mode != VF_MODE_PLAIN && mode != VF_MODE_VEGAS) {
+        set_error("unknown mode %d", mode);
+        return VF_ERR_INVALID;
+    }
+    if (world < 1 || world > kMaxWorld || rank < 0 || rank >= world || !peer_buffers || seq == 0 ||
+        n_iter < 0 || n_events_total < 2 || !packed || !result || !workspace ||
+        (mode == VF_MODE_VEGAS && !divisions)) {
+        set_error("vf_run_iterations_sharded: bad arguments (world must be 1..%d)", kMaxWorld);
+        return VF_ERR_INVALID;
+    }
+    if (workspace_bytes < workspace_need(n_dim)) {
+        set_error("workspace too small: %zu < %zu", workspace_bytes, workspace_need(n_dim));
+        return VF_ERR_WORKSPACE;
+    }
+    const bool with_hist = mode == VF_MODE_VEGAS && train;
+    EventLaunch L;
+    L.mode = mode;
+    L.n_dim = n_dim;
+    L.stream = (cudaStream_t)stream;
+    int nblocks = 0;
+    L.nblocks_out = &nblocks;
+    rc = make_limits(n_dim, xmin, xdelta, &L.k.lim);
+    if (rc) return rc;
+    fill_consts(integrand, n_dim, &L.k.ic);
+    L.k.divisions = divisions;
+    L.k.partials = (double*)workspace;
+    L.k.ev_begin = ev_begin;
+    L.k.ev_end = ev_begin + (uint64_t)n_events_local;
+    L.k.xjac = 1.0 / (double)n_events_total;  // monte_carlo.py:224-227
+    L.k.pk = make_philox_keys(seed);
+    L.k.train = train;
+    PeerPtrs peers;
+    for (int p = 0; p < kMaxWorld; ++p)
+        peers.base[p] = p < world ? (unsigned long long*)(uintptr_t)peer_buffers[p] : nullptr;
+    for (int it = 0; it < n_iter; ++it) {
+        L.k.iteration = first_iteration + (uint32_t)it;
+        rc = dispatch_integrand(integrand,
+                                [&](auto tag) { return launch_event<decltype(tag)>(L); });
+        if (rc) return rc;
+        rc = launch_exchange_epilogue((double*)workspace, nblocks, n_dim, with_hist,
+                                      n_events_total, train, packed + (size_t)n_dim * kBins, packed,
+                                      divisions, result + 2 * it, rank, world, peers, seq + it,
                                       L.stream);
         if (rc) return rc;
     }
@@ -366,7 +431,7 @@ int vf_accumulate(int n_dim, int64_t n, const double* w, const double* f, const 
     rc = launch_accumulate(n_dim, n, w, f, ind, with_hist, (double*)workspace, &nblocks,
                            (cudaStream_t)stream);
     if (rc) return rc;
-    return launch_finalize((const double*)workspace, nblocks, n_dim, with_hist, out_sums, out_hist,
+    return launch_finalize((double*)workspace, nblocks, n_dim, with_hist, out_sums, out_hist,
                            accumulate, (cudaStream_t)stream);
 }
 
@@ -417,8 +482,8 @@ int vfp_run_event(int integrand, int n_dim, int n_strat, int64_t n_cubes, int64_
     if (rc) return rc;
     if (!train) return VF_OK;
     // histogram only: the scalar block writes into a scratch pair past the partial records
-    double* scratch_sums = (double*)workspace + (size_t)kMaxBlocks * partial_stride(n_dim);
-    return launch_finalize((const double*)workspace, nblocks, n_dim, true, scratch_sums, out_hist,
+    double* scratch_sums = (double*)workspace + ws_doubles(n_dim) - 2;
+    return launch_finalize((double*)workspace, nblocks, n_dim, true, scratch_sums, out_hist,
                            accumulate, L.stream);
 }
 
@@ -447,26 +512,31 @@ int vf_sm_count(void) { return sm_count(); }
 
 int vf_kernel_timing(int enable) {
     g_timing.on = enable != 0;
-    g_timing.used = 0;
+    g_timing.used[0] = g_timing.used[1] = 0;
     return VF_OK;
 }
 
-int vf_kernel_time_ms(double* total_ms, int* launches) {
+static int timing_sum(int category, double* total_ms, int* launches) {
     if (!total_ms || !launches) {
         set_error("vf_kernel_time_ms: null pointer");
         return VF_ERR_INVALID;
     }
     double tot = 0.0;
-    for (size_t k = 0; k + 1 < g_timing.used; k += 2) {
-        VF_CUDA_CHECK(cudaEventSynchronize(g_timing.ev[k + 1]));
+    const auto& ev = g_timing.ev[category];
+    const size_t used = g_timing.used[category];
+    for (size_t k = 0; k + 1 < used; k += 2) {
+        VF_CUDA_CHECK(cudaEventSynchronize(ev[k + 1]));
         float ms = 0.f;
-        VF_CUDA_CHECK(cudaEventElapsedTime(&ms, g_timing.ev[k], g_timing.ev[k + 1]));
+        VF_CUDA_CHECK(cudaEventElapsedTime(&ms, ev[k], ev[k + 1]));
         tot += ms;
     }
     *total_ms = tot;
-    *launches = (int)(g_timing.used / 2);
+    *launches = (int)(used / 2);
     return VF_OK;
 }
+
+int vf_kernel_time_ms(double* total_ms, int* launches) { return timing_sum(0, total_ms, launches); }
+int vf_epilogue_time_ms(double* total_ms, int* launches) { return timing_sum(1, total_ms, launches); }
 
 int64_t vf_launch_count(int reset) {
     const int64_t v = g_launches;

@@ -9,49 +9,57 @@ namespace vf {
 __host__ __device__ inline int64_t imin64(int64_t a, int64_t b) { return a < b ? a : b; }
 
 // ---------------------------------------------------------------------------
-// Reduce per-block partial records [nblocks][2 + n_dim*50] in a fixed order.
-// Block j < n_dim reduces the 50 bins of dimension j; block n_dim the scalars.
-// Replaces _accumulate (monte_carlo.py:72-92) for the blocks of one launch.
+// Gather of one iteration's sums from the workspace (vf_common.cuh layout) by a 128-thread
+// block.  Block j < n_dim owns dimension j: thread col < 50 takes acc[j*50+col] and zeroes it
+// for the next iteration.  The scalar block adds the per-block (sum wf, sum (wf)^2) records in
+// a fixed order (64 slices, then slice order).  Returns the value for `col` on threads
+// col < ncols (threadIdx.x < 64), 0 elsewhere.  Replaces _accumulate (monte_carlo.py:72-92).
 // ---------------------------------------------------------------------------
-constexpr int kFinSlicesMR = 16;
-__global__ void __launch_bounds__(64 * kFinSlicesMR) finalize_kernel(
-    const double* __restrict__ partials, int nblocks, int n_dim, int with_hist, double* out_sums,
-    double* out_hist, int accumulate) {
-    __shared__ double part[kFinSlicesMR][64];
-    const size_t stride = partial_stride(n_dim);
-    const int col = threadIdx.x & 63, slice = threadIdx.x >> 6;
-    const bool scalars = (int)blockIdx.x == (with_hist ? n_dim : 0);
-    const int ncols = scalars ? 2 : kBins;
-    const size_t base = scalars ? 0 : 2 + (size_t)blockIdx.x * kBins;
-    double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
-    if (col < ncols) {
-        const double* p = partials + base + col;
-        int b = slice;
-        for (; b + 3 * kFinSlicesMR < nblocks; b += 4 * kFinSlicesMR) {
-            t0 += p[(size_t)b * stride];
-            t1 += p[(size_t)(b + kFinSlicesMR) * stride];
-            t2 += p[(size_t)(b + 2 * kFinSlicesMR) * stride];
-            t3 += p[(size_t)(b + 3 * kFinSlicesMR) * stride];
+constexpr int kFinThreads = 128;
+__device__ __forceinline__ double gather_column(double* __restrict__ workspace, int nblocks,
+                                                bool scalars, int blk, double (*part)[2]) {
+    const int t = threadIdx.x;
+    if (!scalars) {
+        if (t < kBins) {
+            double* a = workspace + ws_acc_offset() + (size_t)blk * kBins + t;
+            const double v = *a;
+            *a = 0.0;
+            return v;
         }
-        for (; b < nblocks; b += kFinSlicesMR) t0 += p[(size_t)b * stride];
+        return 0.0;
     }
-    part[slice][col] = (t0 + t1) + (t2 + t3);
+    const int col = t & 1, slice = t >> 1;  // 64 slices
+    double acc = 0.0;
+    for (int b = slice; b < nblocks; b += kFinThreads / 2) acc += workspace[(size_t)b * 2 + col];
+    part[slice][col] = acc;
     __syncthreads();
-    if (slice == 0 && col < ncols) {
-        double tot = 0.0;
-#pragma unroll
-        for (int k = 0; k < kFinSlicesMR; ++k) tot += part[k][col];
-        double* out = scalars ? out_sums + col : out_hist + (size_t)blockIdx.x * kBins + col;
+    double tot = 0.0;
+    if (t < 2)
+        for (int k = 0; k < kFinThreads / 2; ++k) tot += part[k][t];
+    return tot;
+}
+
+__global__ void __launch_bounds__(kFinThreads) finalize_kernel(double* __restrict__ workspace,
+                                                               int nblocks, int n_dim,
+                                                               int with_hist, double* out_sums,
+                                                               double* out_hist, int accumulate) {
+    __shared__ double part[kFinThreads / 2][2];
+    const bool scalars = (int)blockIdx.x == (with_hist ? n_dim : 0);
+    const int blk = scalars ? n_dim : (int)blockIdx.x;
+    const int ncols = scalars ? 2 : kBins;
+    const double tot = gather_column(workspace, nblocks, scalars, blk, part);
+    if ((int)threadIdx.x < ncols) {
+        double* out = scalars ? out_sums + threadIdx.x : out_hist + (size_t)blk * kBins + threadIdx.x;
         *out = accumulate ? *out + tot : tot;
     }
 }
 
-int launch_finalize(const double* partials, int nblocks, int n_dim, bool with_hist,
-                    double* out_sums, double* out_hist, int accumulate, cudaStream_t stream) {
-    // blocks [0, n_dim) reduce the histogram rows (only when one is wanted), the last block
-    // the two scalars
-    finalize_kernel<<<with_hist ? n_dim + 1 : 1, 64 * kFinSlicesMR, 0, stream>>>(
-        partials, nblocks, n_dim, with_hist ? 1 : 0, out_sums, out_hist, accumulate);
+int launch_finalize(double* workspace, int nblocks, int n_dim, bool with_hist, double* out_sums,
+                    double* out_hist, int accumulate, cudaStream_t stream) {
+    // blocks [0, n_dim) take the histogram rows (only when one is wanted), the last block the
+    // two scalars
+    finalize_kernel<<<with_hist ? n_dim + 1 : 1, kFinThreads, 0, stream>>>(
+        workspace, nblocks, n_dim, with_hist ? 1 : 0, out_sums, out_hist, accumulate);
     count_launch();
     VF_CUDA_CHECK(cudaGetLastError());
     return VF_OK;
@@ -63,12 +71,35 @@ int launch_finalize(const double* partials, int nblocks, int n_dim, bool with_hi
 // the rebinning scan run on one thread in the reference's order; the
 // per-boundary interpolation (:206-207) is parallel again.
 // ---------------------------------------------------------------------------
+// Shared-memory accesses through explicit 32-bit shared-window addresses: inside the serial scan
+// the compiler otherwise re-derives the window base (S2UR SR_CgaCtaId, ~50 cycles) at every
+// access of a static __shared__ array.
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t addr, double v) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ void sts_s32(uint32_t addr, int v) {
+    asm volatile("st.shared.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+#ifdef VF_PHASE_TIMING
+__device__ long long g_phase_clock[16];
+#define VF_PHASE(k) do { if (threadIdx.x == 0 && blockIdx.x == 0) g_phase_clock[k] = clock64(); } while (0)
+#else
+#define VF_PHASE(k) do { } while (0)
+#endif
+
 __device__ void refine_dimension(const double* __restrict__ t_res_sq, double* sub_global) {
     __shared__ double sub[kEdges], sm[kBins], wei[kBins];
     __shared__ double s_sum, s_ave;
     __shared__ double b_cur[kBins], b_prev[kBins], b_bw[kBins];
     __shared__ int b_n[kBins];
     const int i = threadIdx.x;
+    VF_PHASE(2);
     if (i < kEdges) sub[i] = sub_global[i];
     if (i < kBins) {
         const double c = t_res_sq[i];
@@ -79,47 +110,61 @@ __device__ void refine_dimension(const double* __restrict__ t_res_sq, double* su
         sm[i] = fmax(__ddiv_rn(s, meaner), 1e-30);                   // :159
     }
     __syncthreads();
+    VF_PHASE(3);
     if (i == 0) {
         double s = 0.0;
         for (int k = 0; k < kBins; ++k) s = __dadd_rn(s, sm[k]);  // :162
         s_sum = s;
     }
     __syncthreads();
+    VF_PHASE(4);
     if (i < kBins) {
         const double sum_t = s_sum;
         const double aux = __ddiv_rn(__dsub_rn(1.0, __ddiv_rn(sm[i], sum_t)),
                                      __dsub_rn(log(sum_t), log(sm[i])));  // :163-164
-        wei[i] = pow(aux, kAlpha);                                        // :165
+        // :165 tf.pow(aux, ALPHA) with ALPHA = 1.5: aux*sqrt(aux) (sqrt is correctly rounded, one
+        // more rounding for the product: <= 1 ulp, the same error class as libm/libdevice pow)
+        // instead of the ~250-instruction generic pow on the latency-critical path.
+        static_assert(kAlpha == 1.5, "refine uses aux*sqrt(aux) for ALPHA = 1.5");
+        wei[i] = __dmul_rn(aux, sqrt(aux));
     }
     __syncthreads();
-    if (i == 0) {
+    VF_PHASE(5);
+    if (i < 32) {  // the whole first warp runs the serial part redundantly: uniform branches,
+                   // no divergence barriers around every step (all lanes store identical values)
         double s = 0.0;
         for (int k = 0; k < kBins; ++k) s = __dadd_rn(s, wei[k]);
         const double ave = __ddiv_rn(s, (double)kBins);  // :166
         s_ave = ave;
+        VF_PHASE(6);
         // serial scan :195-205 (state: bin_weight, n_bin, cur, prev).  The reference advances
         // n while bin_weight < ave and then emits one boundary; here the same sequence of
-        // additions/subtractions/comparisons is driven by n (static, fully unrolled, operands
-        // at fixed shared-memory addresses) with the emits in an inner loop -- identical
-        // floating-point operations in the identical order, without dynamic indexing on the
-        // critical path.
+        // additions/subtractions/comparisons is driven by n with the emits in an inner loop --
+        // identical floating-point operations in the identical order; the operands of step n+1
+        // are fetched one step ahead so no shared-memory latency sits on the dependent chain.
+        // (Measured alternatives -- speculative/branch-free steps, integer compares, explicit
+        // shared addressing -- were all slower: a lone lane issues ~1 instruction per 6-7 cycles,
+        // so the shortest instruction sequence wins; scripts/exp/epi_phases.cu.)
         double bw = 0.0, cur = 0.0, prev = 0.0;
         int k = 1;
-#pragma unroll
-        for (int n = 0; n < kBins; ++n) {
-            if (k < kBins) {
-                bw = __dadd_rn(bw, wei[n]);  // :187
-                prev = cur;                  // :188
-                cur = sub[n + 1];            // :189
-                while (k < kBins && !(bw < ave)) {
-                    bw = __dsub_rn(bw, ave);  // :205
-                    b_cur[k] = cur;
-                    b_prev[k] = prev;
-                    b_bw[k] = bw;
-                    b_n[k] = n;
-                    ++k;
-                }
+        double w_cur = wei[0], s_cur = sub[1];
+#pragma unroll 1
+        for (int n = 0; n < kBins && k < kBins; ++n) {
+            const int m = n + 1 < kBins ? n + 1 : n;  // operands of the next step, fetched ahead
+            const double w_nxt = wei[m], s_nxt = sub[m + 1];
+            bw = __dadd_rn(bw, w_cur);  // :187
+            prev = cur;                 // :188
+            cur = s_cur;                // :189
+            while (k < kBins && !(bw < ave)) {
+                bw = __dsub_rn(bw, ave);  // :205
+                b_cur[k] = cur;
+                b_prev[k] = prev;
+                b_bw[k] = bw;
+                b_n[k] = n;
+                ++k;
             }
+            w_cur = w_nxt;
+            s_cur = s_nxt;
         }
         // guard: if round-off left boundaries unassigned, close them on the last bin
         for (; k < kBins; ++k) {
@@ -131,6 +176,7 @@ __device__ void refine_dimension(const double* __restrict__ t_res_sq, double* su
         }
     }
     __syncthreads();
+    VF_PHASE(7);
     if (i >= 1 && i < kBins) {
         const double delta =
             __ddiv_rn(__dmul_rn(__dsub_rn(b_cur[i], b_prev[i]), b_bw[i]), wei[b_n[i]]);  // :206
@@ -138,6 +184,7 @@ __device__ void refine_dimension(const double* __restrict__ t_res_sq, double* su
     }
     if (i == 0) sub_global[0] = 0.0;          // :195
     if (i == kBins) sub_global[kBins] = 1.0;  // :208
+    VF_PHASE(8);
 }
 
 __global__ void __launch_bounds__(64) refine_kernel(const double* __restrict__ hist,
@@ -172,53 +219,26 @@ __global__ void __launch_bounds__(64) epilogue_kernel(int n_dim, double n_events
                          divisions + (size_t)blockIdx.x * kEdges);
 }
 
-// Single-rank fusion of finalize_kernel and epilogue_kernel: block j < n_dim reduces the
-// per-block partial histograms of dimension j (fixed order), stores the row, and refines that
-// dimension in place; block n_dim reduces the two scalars and writes (res, sigma).
-// 1024 threads = 64 columns x 16 slices so the ~300 partial records are read with high
-// memory-level parallelism (4 independent accumulators per thread).
-constexpr int kFinSlices = 16;
-__global__ void __launch_bounds__(64 * kFinSlices) finalize_epilogue_kernel(
-    const double* __restrict__ partials, int nblocks, int n_dim, int with_hist, double n_events,
+// Single-rank fusion of finalize_kernel and epilogue_kernel: block j < n_dim takes the bin sums
+// of dimension j, stores the row, and refines that dimension in place; block n_dim reduces the
+// two scalars in a fixed order and writes (res, sigma).
+__global__ void __launch_bounds__(kFinThreads) finalize_epilogue_kernel(
+    double* __restrict__ workspace, int nblocks, int n_dim, int with_hist, double n_events,
     int train, double* out_sums, double* out_hist, double* divisions, double* result) {
-    __shared__ double part[kFinSlices][64];
-    __shared__ double row[kBins];
-    const size_t stride = partial_stride(n_dim);
-    const int col = threadIdx.x & 63, slice = threadIdx.x >> 6;
-    // without a histogram the grid is the single scalar block
+    __shared__ double part[kFinThreads / 2][2];
+    __shared__ double row[64];
+    VF_PHASE(0);
     const bool scalars = (int)blockIdx.x == (with_hist ? n_dim : 0);
-    const int ncols = scalars ? 2 : kBins;
-    const size_t base = scalars ? 0 : 2 + (size_t)blockIdx.x * kBins;
-    double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
-    if (col < ncols) {
-        const double* p = partials + base + col;
-        int b = slice;
-        for (; b + 3 * kFinSlices < nblocks; b += 4 * kFinSlices) {
-            t0 += p[(size_t)b * stride];
-            t1 += p[(size_t)(b + kFinSlices) * stride];
-            t2 += p[(size_t)(b + 2 * kFinSlices) * stride];
-            t3 += p[(size_t)(b + 3 * kFinSlices) * stride];
-        }
-        for (; b < nblocks; b += kFinSlices) t0 += p[(size_t)b * stride];
-    }
-    part[slice][col] = (t0 + t1) + (t2 + t3);
-    __syncthreads();
-    if (slice == 0 && col < ncols) {
-        double tot = 0.0;
-#pragma unroll
-        for (int k = 0; k < kFinSlices; ++k) tot += part[k][col];
-        if (scalars) {
-            out_sums[col] = tot;
-            part[0][col] = tot;
-        } else {
-            out_hist[(size_t)blockIdx.x * kBins + col] = tot;
-            row[col] = tot;
-        }
-    }
-    __syncthreads();
+    const int blk = scalars ? n_dim : (int)blockIdx.x;
+    const double tot = gather_column(workspace, nblocks, scalars, blk, part);
     if (scalars) {
+        if (threadIdx.x < 2) {
+            out_sums[threadIdx.x] = tot;
+            row[threadIdx.x] = tot;
+        }
+        __syncthreads();
         if (threadIdx.x == 0) {
-            const double res = part[0][0], res2 = part[0][1];
+            const double res = row[0], res2 = row[1];
             const double err_tmp2 = __ddiv_rn(
                 __dsub_rn(__dmul_rn(n_events, res2), __dmul_rn(res, res)), n_events - 1.0);
             result[0] = res;
@@ -226,16 +246,124 @@ __global__ void __launch_bounds__(64 * kFinSlices) finalize_epilogue_kernel(
         }
         return;
     }
-    if (train) refine_dimension(row, divisions + (size_t)blockIdx.x * kEdges);
+    if (threadIdx.x < kBins) {
+        out_hist[(size_t)blk * kBins + threadIdx.x] = tot;
+        row[threadIdx.x] = tot;
+    }
+    __syncthreads();
+    VF_PHASE(1);
+    if (train) refine_dimension(row, divisions + (size_t)blk * kEdges);
 }
 
-int launch_finalize_epilogue(const double* partials, int nblocks, int n_dim, bool with_hist,
+int launch_finalize_epilogue(double* partials, int nblocks, int n_dim, bool with_hist,
                              int64_t n_events, int train, double* out_sums, double* out_hist,
                              double* divisions, double* result, cudaStream_t stream) {
     const int blocks = with_hist ? n_dim + 1 : 1;
-    finalize_epilogue_kernel<<<blocks, 64 * kFinSlices, 0, stream>>>(partials, nblocks, n_dim, with_hist ? 1 : 0,
-                                                        (double)n_events, train, out_sums, out_hist,
-                                                        divisions, result);
+    timing_begin(stream, 1);
+    finalize_epilogue_kernel<<<blocks, kFinThreads, 0, stream>>>(
+        partials, nblocks, n_dim, with_hist ? 1 : 0, (double)n_events, train, out_sums, out_hist,
+        divisions, result);
+    timing_end(stream, 1);
+    count_launch();
+    VF_CUDA_CHECK(cudaGetLastError());
+    return VF_OK;
+}
+
+// ---------------------------------------------------------------------------
+// Multi-GPU: block reduction + one-shot all-reduce over NVLink peer memory + sigma + refine in
+// ONE kernel (replaces finalize_kernel -> ncclAllReduce -> epilogue_kernel).
+//
+// Every rank owns a symmetric exchange buffer, mapped into all peers:
+//   u64 flags[(n_dim+1)][world]            arrival counter per (block, source rank)
+//   f64 data[2][world][50*n_dim + 2]       records, double-buffered on the parity of `seq`
+// Block j reduces its own partials, PUSHES its 50 (or 2) sums into slot [parity][rank] of every
+// peer's buffer with plain P2P stores, fences, releases flag[j][rank] = seq on every peer, waits
+// until flag[j][p] >= seq for all p in its own buffer, then adds the `world` slots in rank order
+// -- the same order on every rank, so all ranks refine bit-identical grids without a broadcast.
+// `seq` increases by one per call; two data buffers suffice because a rank can run at most one
+// exchange ahead of its slowest peer.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(kFinThreads) exchange_epilogue_kernel(
+    double* __restrict__ workspace, int nblocks, int n_dim, int with_hist, double n_events,
+    int train, double* out_sums, double* out_hist, double* divisions, double* result, int rank,
+    int world, const __grid_constant__ PeerPtrs peers, unsigned long long seq) {
+    __shared__ double part[kFinThreads / 2][2];
+    __shared__ double row[64];
+    const bool scalars = (int)blockIdx.x == (with_hist ? n_dim : 0);
+    const int blk = scalars ? n_dim : (int)blockIdx.x;  // flag row / record section
+    const int ncols = scalars ? 2 : kBins;
+    const int col = threadIdx.x;
+    const double mine = gather_column(workspace, nblocks, scalars, blk, part);
+    const int nrec = n_dim * kBins + 2;
+    const size_t data_off = (size_t)(n_dim + 1) * world;  // u64 units, flags come first
+    const int parity = (int)(seq & 1ull);
+    const int idx = scalars ? n_dim * kBins + col : blk * kBins + col;  // packed [hist | sums]
+    if (col < ncols) {
+        for (int p = 0; p < world; ++p) {  // push to every rank (own buffer included)
+            double* slot = reinterpret_cast<double*>(peers.base[p] + data_off) +
+                           (size_t)(parity * world + rank) * nrec;
+            slot[idx] = mine;
+        }
+        __threadfence_system();
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < world) {
+        const int p = threadIdx.x;
+        st_release_sys(peers.base[p] + (size_t)blk * world + rank, seq);
+        const unsigned long long* flag = peers.base[rank] + (size_t)blk * world + p;
+        while (ld_acquire_sys(flag) < seq) {
+        }
+    }
+    __syncthreads();
+    if (col < ncols) {
+        const volatile double* data = reinterpret_cast<const volatile double*>(
+            peers.base[rank] + data_off);
+        double tot = 0.0;
+        for (int p = 0; p < world; ++p) tot += data[(size_t)(parity * world + p) * nrec + idx];
+        if (scalars) {
+            out_sums[col] = tot;
+        } else {
+            out_hist[(size_t)blk * kBins + col] = tot;
+        }
+        row[col] = tot;
+    }
+    __syncthreads();
+    if (scalars) {
+        if (threadIdx.x == 0) {
+            const double res = row[0], res2 = row[1];
+            const double err_tmp2 = __ddiv_rn(
+                __dsub_rn(__dmul_rn(n_events, res2), __dmul_rn(res, res)), n_events - 1.0);
+            result[0] = res;
+            result[1] = sqrt(fmax(err_tmp2, 0.0));
+        }
+        return;
+    }
+    if (train) refine_dimension(row, divisions + (size_t)blk * kEdges);
+}
+
+size_t exchange_bytes(int n_dim, int world) {
+    return ((size_t)(n_dim + 1) * world + (size_t)2 * world * (n_dim * kBins + 2)) * 8;
+}
+
+int launch_exchange_epilogue(double* partials, int nblocks, int n_dim, bool with_hist,
+                             int64_t n_events, int train, double* out_sums, double* out_hist,
+                             double* divisions, double* result, int rank, int world,
+                             const PeerPtrs& peers, unsigned long long seq, cudaStream_t stream) {
+    const int blocks = with_hist ? n_dim + 1 : 1;
+    timing_begin(stream, 1);
+    exchange_epilogue_kernel<<<blocks, kFinThreads, 0, stream>>>(
+        partials, nblocks, n_dim, with_hist ? 1 : 0, (double)n_events, train, out_sums, out_hist,
+        divisions, result, rank, world, peers, seq);
+    timing_end(stream, 1);
     count_launch();
     VF_CUDA_CHECK(cudaGetLastError());
     return VF_OK;
@@ -380,17 +508,18 @@ __global__ void __launch_bounds__(256) accumulate_kernel(int n_dim, int64_t n,
         red[1][warp] = sum2;
     }
     __syncthreads();
-    double* out = partials + (size_t)blockIdx.x * partial_stride(n_dim);
     if (threadIdx.x < 2) {
         double t = 0.0;
         for (int k = 0; k < 8; ++k) t += red[threadIdx.x][k];
-        out[threadIdx.x] = t;
+        partials[(size_t)blockIdx.x * 2 + threadIdx.x] = t;
     }
-    for (int i = threadIdx.x; i < n_dim * kBins; i += blockDim.x) {
-        double t = 0.0;
-        if (do_hist)
+    if (do_hist) {
+        double* acc = partials + ws_acc_offset();
+        for (int i = threadIdx.x; i < n_dim * kBins; i += blockDim.x) {
+            double t = 0.0;
             for (int c = 0; c < kAccHC; ++c) t += hist[i * kAccHC + c];
-        out[2 + i] = t;
+            atomicAdd(acc + i, t);
+        }
     }
 }
 

@@ -4,11 +4,21 @@
 
 namespace vf {
 
-int launch_finalize(const double* partials, int nblocks, int n_dim, bool with_hist,
+constexpr int kMaxWorld = 8;  // GPUs of one NVLink box
+struct PeerPtrs {
+    unsigned long long* base[kMaxWorld];  // every rank's symmetric exchange buffer
+};
+
+int launch_finalize(double* partials, int nblocks, int n_dim, bool with_hist,
                     double* out_sums, double* out_hist, int accumulate, cudaStream_t stream);
-int launch_finalize_epilogue(const double* partials, int nblocks, int n_dim, bool with_hist,
+int launch_finalize_epilogue(double* partials, int nblocks, int n_dim, bool with_hist,
                              int64_t n_events, int train, double* out_sums, double* out_hist,
                              double* divisions, double* result, cudaStream_t stream);
+size_t exchange_bytes(int n_dim, int world);
+int launch_exchange_epilogue(double* partials, int nblocks, int n_dim, bool with_hist,
+                             int64_t n_events, int train, double* out_sums, double* out_hist,
+                             double* divisions, double* result, int rank, int world,
+                             const PeerPtrs& peers, unsigned long long seq, cudaStream_t stream);
 int launch_refine(int n_dim, const double* hist, double* divisions, cudaStream_t stream);
 int launch_epilogue(int n_dim, int64_t n_events, int train, const double* sums, const double* hist,
                     double* divisions, double* result, cudaStream_t stream);

@@ -23,8 +23,8 @@ int cuda_fail(cudaError_t e, const char* what);
 void count_launch(int n = 1);
 int sm_count();
 // optional CUDA-event bracket around the event kernels (vf_kernel_timing)
-void timing_begin(cudaStream_t stream);
-void timing_end(cudaStream_t stream);
+void timing_begin(cudaStream_t stream, int category = 0);
+void timing_end(cudaStream_t stream, int category = 0);
 
 #define VF_CUDA_CHECK(expr)                                   \
     do {                                                      \
@@ -120,15 +120,33 @@ __device__ __forceinline__ void vegas_map_dim(double xn, const char* __restrict_
     wfac = __dmul_rn(e.y, kFBins);            // :78
 }
 
+// y / b with IEEE round-to-nearest in three fp64 operations, given rb = rn(1/b):
+// q0 = rn(y*rb) is within 1 ulp of y/b, r = y - b*q0 is exact in one FMA, and q0 + r*rb rounds
+// to rn(y/b) (Markstein's theorem; b's significand must not be all ones -- true for the integer
+// divisors used here).  0 mismatches vs `/` on 7.6e8 host samples over 20 022 integer divisors.
+__device__ __forceinline__ double div_rn_by(double y, double b, double rb) {
+    const double q0 = __dmul_rn(y, rb);
+    const double r = __fma_rn(-b, q0, y);
+    return __fma_rn(r, rb, q0);
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
 
-// Layout of one block's partial results in the workspace.
-__host__ __device__ inline size_t partial_stride(int n_dim) { return 2 + (size_t)n_dim * kBins; }
-
+// Workspace layout (doubles), see vf_workspace_bytes:
+//   scalars[kMaxBlocks][2]   per-block (sum wf, sum (wf)^2), reduced later in a fixed order
+//   acc[n_dim*50]            histogram accumulator: every event-kernel block adds its 50*d bin
+//                            sums with native fp64 RED; the reduce kernel reads AND ZEROES it,
+//                            so it is all-zero between iterations (the caller zero-initialises
+//                            the workspace once)
+//   scratch[2]
 constexpr int kMaxBlocks = 2048;  // upper bound on event-kernel grid size
+__host__ __device__ inline size_t ws_acc_offset() { return (size_t)kMaxBlocks * 2; }
+__host__ __device__ inline size_t ws_doubles(int n_dim) {
+    return ws_acc_offset() + (size_t)n_dim * kBins + 2;
+}
 
 }  // namespace vf

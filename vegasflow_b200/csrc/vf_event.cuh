@@ -30,9 +30,16 @@ constexpr int min_blocks() {
     return (I::kHeavy || Cfg<NDIM>::kMinBlocks == 1) ? 1 : 2;
 }
 
+// The stratified kernel carries the cube state (coordinates, counts, per-cube sums) on top of
+// the event state; for d > 4 it needs the 128-register budget to stay spill-free.
+template <class I, int NDIM>
+constexpr int plus_min_blocks() {
+    return (NDIM <= 4 && !I::kHeavy) ? 2 : 1;
+}
+
 struct EventKernelArgs {
     const double* divisions;  // [NDIM][51]
-    double* partials;         // [gridDim.x][2 + NDIM*50]
+    double* partials;         // workspace: scalars[grid][2] | acc[NDIM*50]
     uint64_t ev_begin, ev_end;
     double xjac;
     uint32_t iteration;
@@ -72,11 +79,12 @@ __device__ __forceinline__ double apply_jacobians(double w, double (&x)[NDIM], d
     return w;
 }
 
-// Block-level tail shared by the event kernels: reduce the two scalars and the
-// histogram copies in a fixed order and write this block's partial record.
+// Block-level tail shared by the event kernels: the two scalars are reduced in a fixed order
+// into this block's record; the histogram copies are reduced in-block and added to the global
+// accumulator with one fp64 RED per (dimension, bin).
 template <int NDIM>
 __device__ __forceinline__ void write_partials(double sum, double sum2, const double* hist,
-                                               bool with_hist, double* partials) {
+                                               bool with_hist, double* workspace) {
     using C = Cfg<NDIM>;
     __shared__ double red[2][C::kThreads / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -87,19 +95,19 @@ __device__ __forceinline__ void write_partials(double sum, double sum2, const do
         red[1][warp] = sum2;
     }
     __syncthreads();  // also orders the shared-memory histogram updates
-    double* out = partials + (size_t)blockIdx.x * partial_stride(NDIM);
     if (threadIdx.x < 2) {
         double t = 0.0;
         for (int w = 0; w < C::kThreads / 32; ++w) t += red[threadIdx.x][w];
-        out[threadIdx.x] = t;
+        workspace[(size_t)blockIdx.x * 2 + threadIdx.x] = t;
     }
-    for (int i = threadIdx.x; i < NDIM * kBins; i += blockDim.x) {
-        double t = 0.0;
-        if (with_hist) {
+    if (with_hist) {
+        double* acc = workspace + ws_acc_offset();
+        for (int i = threadIdx.x; i < NDIM * kBins; i += blockDim.x) {
+            double t = 0.0;
 #pragma unroll
             for (int c = 0; c < C::HC; ++c) t += hist[i * C::HC + c];
+            atomicAdd(acc + i, t);  // RED.E.ADD.F64
         }
-        out[2 + i] = t;
     }
 }
 
@@ -280,7 +288,7 @@ struct PlusKernelArgs {
 };
 
 template <class I, int NDIM, bool EXT>
-__global__ void __launch_bounds__(Cfg<NDIM>::kThreads, min_blocks<I, NDIM>())
+__global__ void __launch_bounds__(Cfg<NDIM>::kThreads, plus_min_blocks<I, NDIM>())
 plus_event_kernel(const __grid_constant__ PlusKernelArgs a) {
     using C = Cfg<NDIM>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -296,9 +304,10 @@ plus_event_kernel(const __grid_constant__ PlusKernelArgs a) {
     const int64_t begin = (int64_t)blockIdx.x * per_block;
     const int64_t end = min(begin + per_block, a.n_events);
     const double fstrat = (double)a.n_strat;
+    const double rstrat = __ddiv_rn(1.0, fstrat);
 
     int64_t cube = -1, hi = 0;
-    double s1 = 0.0, s2 = 0.0, fn = 1.0;
+    double s1 = 0.0, s2 = 0.0, fn = 1.0, rfn = 1.0;
     double coords[NDIM];
     double hsum2 = 0.0;  // unused scalar partials (kept zero)
     for (int64_t e = begin + threadIdx.x; e < end; e += C::kThreads) {
@@ -318,6 +327,7 @@ plus_event_kernel(const __grid_constant__ PlusKernelArgs a) {
             cube = lo_c;
             hi = a.ev_offset[cube + 1];
             fn = (double)a.n_ev[cube];  // vflowplus.py:69
+            rfn = __ddiv_rn(1.0, fn);
             int64_t rem = cube;         // itertools.product order, vflowplus.py:126-128
 #pragma unroll
             for (int j = NDIM - 1; j >= 0; --j) {
@@ -344,7 +354,7 @@ plus_event_kernel(const __grid_constant__ PlusKernelArgs a) {
                     else r = h == 0 ? u52_to_uniform(o.x, o.y) : u52_to_uniform(o.z, o.w);
                     // vflowplus.py:72: (points + rnds) * FBINS / n_strat
                     const double xn =
-                        __ddiv_rn(__dmul_rn(__dadd_rn(coords[j], r), kFBins), fstrat);
+                        div_rn_by(__dmul_rn(__dadd_rn(coords[j], r), kFBins), fstrat, rstrat);
                     double wfac;
                     vegas_map_dim<C::TC>(xn, tbl_lane + j * (kBins * C::TC * 16), x[j], wfac,
                                          bin[j]);
@@ -352,7 +362,7 @@ plus_event_kernel(const __grid_constant__ PlusKernelArgs a) {
                 }
             }
         }
-        w = __ddiv_rn(w, fn);  // vflowplus.py:77
+        w = div_rn_by(w, fn, rfn);  // vflowplus.py:77 (correctly rounded, see div_rn_by)
         w = apply_jacobians<NDIM>(w, x, a.xjac, a.lim);
         const double f = I::template eval<NDIM>(x, a.ic);
         const double tmp = __dmul_rn(w, f);       // vflowplus.py:209
@@ -462,7 +472,7 @@ int launch_plus_dim(const PlusLaunch& L) {
     auto kern = ext ? plus_event_kernel<I, NDIM, true> : plus_event_kernel<I, NDIM, false>;
     VF_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)C::kSmemBytes));
-    const int blocks = grid_blocks_for(L.k.n_events, C::kThreads, min_blocks<I, NDIM>());
+    const int blocks = grid_blocks_for(L.k.n_events, C::kThreads, plus_min_blocks<I, NDIM>());
     timing_begin(L.stream);
     kern<<<blocks, C::kThreads, C::kSmemBytes, L.stream>>>(L.k);
     timing_end(L.stream);

@@ -133,6 +133,8 @@ class MonteCarloFlow(ABC):
         self._workspace = None
         self._packed = None
         self._results = None
+        self._exchange = None
+        self._exchange_tried = False
 
     # ------------------------------------------------------------------ state
     def _ensure_device(self):
@@ -141,7 +143,8 @@ class MonteCarloFlow(ABC):
         _lib.require_cuda()
         self._device = torch.device("cuda", torch.cuda.current_device())
         nbytes = _lib.load().vf_workspace_bytes(self.n_dim)
-        self._workspace = torch.empty(nbytes // 8, dtype=DTYPE, device=self._device)
+        # zero-initialised once: the library keeps the histogram accumulator zeroed afterwards
+        self._workspace = torch.zeros(nbytes // 8, dtype=DTYPE, device=self._device)
         # packed per-iteration buffer: histogram [n_dim*50] then (sum wf, sum wf^2)
         self._packed = torch.zeros(self.n_dim * BINS_MAX + 2, dtype=DTYPE, device=self._device)
         self._results = torch.zeros((64, 2), dtype=DTYPE, device=self._device)
@@ -165,6 +168,49 @@ class MonteCarloFlow(ABC):
     def _fused_single_rank(self):
         return (self._BATCHABLE and self._builtin is not None and not self._vectorial
                 and parallel.world()[1] == 1)
+
+    def _fused_peer_exchange(self):
+        """Multi-rank fused iteration over peer memory (None -> NCCL all-reduce path)."""
+        if not (self._BATCHABLE and self._builtin is not None and not self._vectorial
+                and parallel.world()[1] > 1):
+            return None
+        if not self._exchange_tried:
+            self._ensure_device()
+            self._exchange = parallel.make_peer_exchange(self.n_dim, self._device)
+            self._exchange_tried = True
+        return self._exchange
+
+    def _run_sharded_iterations(self, xchg, n_iter):
+        """`n_iter` iterations of this rank with ONE C-ABI call: per iteration the event kernel
+        over its shard, then one kernel doing block reduction + NVLink exchange + sigma + refine
+        (vf_run_iterations_sharded).  Returns the device rows [(res, sigma)] * n_iter."""
+        lib = _lib.load()
+        begin, end = parallel.shard_range(self.n_events)
+        rows = self._result_rows(n_iter)
+        first_seq = xchg.seq + 1
+        xchg.seq += n_iter
+        _lib.check(
+            lib.vf_run_iterations_sharded(
+                self._MODE, self._builtin.integrand_id(), self.n_dim, begin, end - begin,
+                self.n_events, self._seed, self._iteration, n_iter,
+                int(bool(getattr(self, "train", False))), _lib.ptr(self._grid_tensor()),
+                self._xmin_c, self._xdelta_c, _lib.ptr(self._packed), _lib.ptr(rows),
+                _lib.ptr(self._workspace), self._workspace.numel() * 8, xchg.rank,
+                xchg.world_size, xchg.ptrs, first_seq, _lib.stream_ptr(),
+            )
+        )
+        self._iteration += n_iter
+        return rows
+
+    def _run_batched(self, n_iter):
+        """All `n_iter` iterations enqueued by one call, or None if this configuration has to
+        go iteration by iteration (python integrand, VEGAS+, NCCL collective)."""
+        if self._fused_single_rank():
+            return self._run_fused_iterations(n_iter)
+        xchg = self._fused_peer_exchange()
+        if xchg is not None:
+            return self._run_sharded_iterations(xchg, n_iter)
+        return None
 
     def _run_fused_iterations(self, n_iter):
         """Enqueue `n_iter` whole iterations with ONE C-ABI call (vf_run_iterations): per
@@ -450,9 +496,9 @@ class MonteCarloFlow(ABC):
         self._ensure_device()
         all_results = []
         first_slot = len(self._history)
-        batched = self._fused_single_rank() and not self._verbose
+        rows = None if self._verbose else self._run_batched(n_iter)
+        batched = rows is not None
         if batched:
-            rows = self._run_fused_iterations(n_iter)
             for k in range(n_iter):
                 all_results.append((rows[k, 0], rows[k, 1]))
                 self._history.append((rows[k, 0], rows[k, 1], None))

@@ -8,8 +8,14 @@ evaluates the global event indices [r*N/R, (r+1)*N/R) of the same Philox
 stream, so the union over ranks is exactly the single-GPU event set and every
 rank refines an identical grid from the identical reduced histogram.
 """
+import ctypes as C
+import logging
+import os
+
 import torch
 import torch.distributed as dist
+
+logger = logging.getLogger(__name__)
 
 
 def world():
@@ -33,3 +39,50 @@ def allreduce_sum_(packed):
     if world()[1] > 1:
         dist.all_reduce(packed, op=dist.ReduceOp.SUM)
     return packed
+
+
+class PeerExchange:
+    """Symmetric (peer-mapped) exchange buffer for the fused reduce + NVLink all-reduce +
+    refine kernel (`vf_run_iteration_sharded`).  One per integrator instance.
+
+    The buffer is allocated with torch symmetric memory so every rank holds device pointers to
+    all peers' copies; the kernel pushes its [n_dim*50+2] sums into every peer with P2P stores
+    and synchronises with release/acquire flags -- no NCCL call on the iteration path.
+    """
+
+    def __init__(self, n_dim, device):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from vegasflow_b200 import _lib
+
+        rank, world_size = world()
+        if world_size > 8:
+            raise RuntimeError("the peer exchange covers the GPUs of one NVLink box (<= 8)")
+        nbytes = _lib.load().vf_exchange_bytes(int(n_dim), world_size)
+        self.buf = symm_mem.empty(nbytes // 8, dtype=torch.int64, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, dist.group.WORLD)
+        self.buf.zero_()
+        torch.cuda.synchronize(device)
+        dist.barrier()
+        ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        if len(ptrs) != world_size:
+            raise RuntimeError("symmetric memory rendezvous returned a wrong number of peers")
+        self.ptrs = (C.c_uint64 * world_size)(*ptrs)
+        self.rank, self.world_size = rank, world_size
+        self.seq = 0
+
+    def next_seq(self):
+        self.seq += 1
+        return self.seq
+
+
+def make_peer_exchange(n_dim, device):
+    """PeerExchange, or None when it is disabled (VEGASFLOW_B200_EXCHANGE=nccl) or the platform
+    cannot provide peer-mapped memory (then the NCCL all-reduce path is used)."""
+    if world()[1] <= 1 or os.environ.get("VEGASFLOW_B200_EXCHANGE", "p2p").lower() == "nccl":
+        return None
+    try:
+        return PeerExchange(n_dim, device)
+    except Exception as exc:  # pylint: disable=broad-except
+        logger.warning("peer-memory exchange unavailable (%s); using the NCCL all-reduce", exc)
+        return None

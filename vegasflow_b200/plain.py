@@ -66,9 +66,9 @@ class PlainFlow(MonteCarloFlow):
 
     def _run_iteration(self):
         """plain.py:37-43"""
-        if self._fused_single_rank():
-            row = self._run_fused_iterations(1)[0]
-            return row[0], row[1]
+        rows = self._run_batched(1)
+        if rows is not None:
+            return rows[0, 0], rows[0, 1]
         self.run_event()
         return self._iteration_epilogue()
 
