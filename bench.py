@@ -227,7 +227,11 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+
+        # short collective timeout: a hang must fail fast, not hold 8 GPUs for 10 minutes
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank),
+                                timeout=datetime.timedelta(seconds=90))
     lib = _lib.require_cuda()
     K, W = args.steps, max(args.warmup, 3)
 
@@ -245,16 +249,35 @@ def main():
     inst = make_instance(wl, world)
     n_step_total = inst.n_events  # whole-job events per step (all ranks)
 
-    # ---- warm-up: W steps, then keep stepping for ~0.3 s so clocks are at load level
-    for _ in range(W):
-        inst._run_iteration()
-    torch.cuda.synchronize()
+    def run_n(n):
+        """n steps of the product path (identical count on every rank)."""
+        n_per_step = inst.n_events
+        if n <= 0:
+            return 0
+        if inst._run_batched(n) is not None:
+            return n_per_step * n
+        done = 0
+        for _ in range(n):
+            done += inst.n_events
+            inst._run_iteration()
+        return done
+
+    def agree_max(x):
+        """Same value on every rank (max), so loop counts derived from it cannot diverge --
+        a rank-dependent iteration count would deadlock the per-iteration collective."""
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- warm-up: W steps (timed to size the clock ramp), then ~0.3 s more of the same steps
+    barrier()
     t0 = time.perf_counter()
-    extra = 0
-    while time.perf_counter() - t0 < 0.3 and extra < 1000:
-        inst._run_iteration()
-        torch.cuda.synchronize()
-        extra += 1
+    run_n(W)
+    barrier()
+    step_s = agree_max((time.perf_counter() - t0) / W)
+    run_n(int(min(2000, max(0, 0.3 / max(step_s, 1e-6)))))
+    barrier()
 
     # ---- timed region: exactly K steps of the product path, device-timed, max over ranks.
     # Single rank: ONE vf_run_iterations call enqueues all K iterations (2 launches each).
@@ -264,14 +287,7 @@ def main():
     ev1 = torch.cuda.Event(enable_timing=True)
     events_done = 0
     def run_steps():
-        n_per_step = inst.n_events
-        if inst._run_batched(K) is not None:
-            return n_per_step * K
-        done = 0
-        for _ in range(K):
-            done += inst.n_events
-            inst._run_iteration()
-        return done
+        return run_n(K)
 
     barrier()
     lib.vf_launch_count(1)
@@ -281,7 +297,8 @@ def main():
     ev1.record()
     barrier()
     launches = int(lib.vf_launch_count(0))
-    ms = ev0.elapsed_time(ev1)
+    ms = agree_max(ev0.elapsed_time(ev1))  # max over ranks
+    value = events_done / (ms * 1e-3)
     # Second, identical K-step pass with the library's CUDA-event bracket around every
     # event-kernel / epilogue launch (same stream): per-kernel durations for the roofline.
     # Kept out of the timed region above because the extra event records widen the gaps
@@ -291,25 +308,19 @@ def main():
     barrier()
     kt, kn = ctypes.c_double(0.0), ctypes.c_int(0)
     _lib.check(lib.vf_kernel_time_ms(ctypes.byref(kt), ctypes.byref(kn)))
-    # keep the same loop running ~1 s more so the clock sampler sees the kernel under load
-    if sampler.nv is not None and ms < 1000.0:
-        t0 = time.perf_counter()
-        while time.perf_counter() - t0 < 1.0:
-            inst._run_iteration()
-            torch.cuda.synchronize()
-    clocks = sampler.stop()
-    clocks["note"] = ("NVML samples every 2 ms over the timed region plus a 1 s repeat of the same "
-                      "loop right after it" if ms < 1000.0 else "NVML samples over the timed region")
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
     et, en = ctypes.c_double(0.0), ctypes.c_int(0)
     _lib.check(lib.vf_epilogue_time_ms(ctypes.byref(et), ctypes.byref(en)))
+    lib.vf_kernel_timing(0)
     kern_ms = kt.value / max(kn.value, 1)
     epi_ms = et.value / max(en.value, 1) if en.value else None
-    lib.vf_kernel_timing(0)
-    value = events_done / (ms * 1e-3)
+    # keep the same steps running ~1 s more so the clock sampler sees the kernel under load
+    # (count derived from the agreed step time: identical on every rank)
+    if ms < 1000.0 and agree_max(1.0 if sampler.nv is not None else 0.0) > 0.5:
+        run_n(int(min(20000, 1000.0 / max(ms / K, 1e-3))))
+        barrier()
+    clocks = sampler.stop()
+    clocks["note"] = ("NVML samples every 2 ms over the timed region plus a ~1 s repeat of the same "
+                      "steps right after it" if ms < 1000.0 else "NVML samples over the timed region")
 
     # ---- e2e: public API, one D2H read of (res, sigma) per step like the reference's logging
     inst2 = make_instance(wl, world)

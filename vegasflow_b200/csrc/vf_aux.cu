@@ -276,6 +276,7 @@ int launch_finalize_epilogue(double* partials, int nblocks, int n_dim, bool with
 // Every rank owns a symmetric exchange buffer, mapped into all peers:
 //   u64 flags[(n_dim+1)][world]            arrival counter per (block, source rank)
 //   f64 data[2][world][50*n_dim + 2]       records, double-buffered on the parity of `seq`
+//   u64 poison                             set when a wait timed out (peer missing)
 // Block j reduces its own partials, PUSHES its 50 (or 2) sums into slot [parity][rank] of every
 // peer's buffer with plain P2P stores, fences, releases flag[j][rank] = seq on every peer, waits
 // until flag[j][p] >= seq for all p in its own buffer, then adds the `world` slots in rank order
@@ -283,6 +284,7 @@ int launch_finalize_epilogue(double* partials, int nblocks, int n_dim, bool with
 // `seq` increases by one per call; two data buffers suffice because a rank can run at most one
 // exchange ahead of its slowest peer.
 // ---------------------------------------------------------------------------
+constexpr long long kExchangeTimeoutCycles = 20000000000ll;  // ~10 s at 2 GHz
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -316,19 +318,32 @@ __global__ void __launch_bounds__(kFinThreads) exchange_epilogue_kernel(
         __threadfence_system();
     }
     __syncthreads();
+    // A peer that never arrives (crashed rank, mismatched iteration counts) must not hang the
+    // GPU: the wait is bounded (~10 s); on expiry the local buffer is marked poisoned, this and
+    // every later exchange on it return NaN immediately, and the caller sees the failure.
+    unsigned long long* poison = peers.base[rank] + data_off + (size_t)2 * world * nrec;
     if ((int)threadIdx.x < world) {
         const int p = threadIdx.x;
         st_release_sys(peers.base[p] + (size_t)blk * world + rank, seq);
         const unsigned long long* flag = peers.base[rank] + (size_t)blk * world + p;
-        while (ld_acquire_sys(flag) < seq) {
+        if (ld_acquire_sys(poison) == 0ull) {
+            const long long t_start = clock64();
+            while (ld_acquire_sys(flag) < seq) {
+                if (clock64() - t_start > kExchangeTimeoutCycles) {
+                    st_release_sys(poison, 1ull);
+                    break;
+                }
+            }
         }
     }
     __syncthreads();
+    const bool poisoned = ld_acquire_sys(poison) != 0ull;
     if (col < ncols) {
         const volatile double* data = reinterpret_cast<const volatile double*>(
             peers.base[rank] + data_off);
         double tot = 0.0;
         for (int p = 0; p < world; ++p) tot += data[(size_t)(parity * world + p) * nrec + idx];
+        if (poisoned) tot = __longlong_as_double(0x7ff8000000000000ll);  // NaN
         if (scalars) {
             out_sums[col] = tot;
         } else {
@@ -347,11 +362,12 @@ __global__ void __launch_bounds__(kFinThreads) exchange_epilogue_kernel(
         }
         return;
     }
-    if (train) refine_dimension(row, divisions + (size_t)blk * kEdges);
+    if (train && !poisoned) refine_dimension(row, divisions + (size_t)blk * kEdges);
 }
 
 size_t exchange_bytes(int n_dim, int world) {
-    return ((size_t)(n_dim + 1) * world + (size_t)2 * world * (n_dim * kBins + 2)) * 8;
+    // flags | double-buffered records | poison word
+    return ((size_t)(n_dim + 1) * world + (size_t)2 * world * (n_dim * kBins + 2) + 1) * 8;
 }
 
 int launch_exchange_epilogue(double* partials, int nblocks, int n_dim, bool with_hist,
