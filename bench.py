@@ -182,16 +182,20 @@ def _profiled_traffic(workload):
         return None
 
 
+RNG_BITS = 52
+
+
 def make_instance(wl, world):
     import vegasflow_b200 as vf
 
     n_total = wl["n_events"] * (world if wl["alg"] != "plus" else 1)
     if wl["alg"] == "vegas":
-        inst = vf.VegasFlow(wl["n_dim"], n_total, verbose=False)
+        inst = vf.VegasFlow(wl["n_dim"], n_total, verbose=False, rng_bits=RNG_BITS)
     elif wl["alg"] == "plus":
-        inst = vf.VegasFlowPlus(wl["n_dim"], n_total, adaptive=True, verbose=False)
+        inst = vf.VegasFlowPlus(wl["n_dim"], n_total, adaptive=True, verbose=False,
+                                rng_bits=RNG_BITS)
     else:
-        inst = vf.PlainFlow(wl["n_dim"], n_total, verbose=False)
+        inst = vf.PlainFlow(wl["n_dim"], n_total, verbose=False, rng_bits=RNG_BITS)
     inst.set_seed(2024)
     inst.compile(getattr(vf.integrands, wl["integrand"]))
     return inst
@@ -205,8 +209,12 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--rng-bits", type=int, default=52, choices=[52, 32],
+                    help="Philox bits per uniform (52 = default stream)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
+    global RNG_BITS
+    RNG_BITS = args.rng_bits
     if args.impl == "reference":
         run_reference_arm(args, wl)
         return
@@ -360,7 +368,7 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
                 "workload": wl["name"], "events_per_step_per_gpu": per_gpu_events,
-                "train": True, "rng": "philox4x32-10, 52-bit uniforms, generated in-kernel",
+                "train": True, "rng": f"philox4x32-10, {RNG_BITS}-bit uniforms, generated in-kernel",
                 "collective": ("none (1 GPU)" if world == 1 else
                                "fused block-reduce + NVLink peer-memory all-reduce + refine kernel"
                                if getattr(inst, "_exchange", None) is not None else

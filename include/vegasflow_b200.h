@@ -24,7 +24,8 @@
  *   - grid layout: divisions[n_dim][51] row-major (src/vegasflow/vflow.py:239-242);
  *     histogram arr_res2[n_dim][50] row-major (vflow.py:387).
  *   - random stream: Philox4x32-10, key = seed, counter =
- *     (event_lo, event_hi, dim_pair, iteration); 52-bit mantissa fill;
+ *     (event_lo, event_hi, block, iteration); block b feeds dimensions 2b, 2b+1 with a 52-bit
+ *     mantissa fill each (default) or 4b..4b+3 with 32 bits each (VF_MODE_RNG32 / rng_bits 32);
  *     r = TECH_CUT + u*(1-2*TECH_CUT) (monte_carlo.py:264-266 semantics).
  */
 #ifndef VEGASFLOW_B200_H
@@ -43,6 +44,10 @@ extern "C" {
 /* sampling modes */
 #define VF_MODE_PLAIN 0 /* PlainFlow, src/vegasflow/plain.py:18-35 */
 #define VF_MODE_VEGAS 1 /* VegasFlow, src/vegasflow/vflow.py:389-430 */
+/* OR'ed into a `mode` argument: draw FOUR 32-bit-resolution uniforms per Philox block instead
+ * of two 52-bit ones (half the integer-multiply work; resolution 2.3e-10 << TECH_CUT = 1e-8).
+ * Off by default: the default stream fills all 52 mantissa bits like tf.random.uniform. */
+#define VF_MODE_RNG32 0x100
 
 /* built-in integrand ids (vf_integrand_id) */
 #define VF_INTEGRAND_SYMGAUSS 0     /* examples/simgauss_tf.py:22-32 */
@@ -172,9 +177,9 @@ int vf_digest_from_uniforms(int mode, int integrand, int n_dim, int64_t n,
                             double* w /*[dev] [n]*/, int32_t* ind /*[dev] [n][n_dim]*/,
                             double* wf /*[dev] [n]*/, void* stream);
 
-/* The engine's uniforms for events [ev_begin, ev_begin+n): rnds [n][n_dim]. */
+/* The engine's uniforms for events [ev_begin, ev_begin+n): rnds [n][n_dim]; rng_bits 52 | 32. */
 int vf_uniforms(int n_dim, uint64_t ev_begin, int64_t n, uint64_t seed, uint32_t iteration,
-                double* rnds /*[dev]*/, void* stream);
+                int rng_bits, double* rnds /*[dev]*/, void* stream);
 
 /*
  * Unfused path for integrands that are not built in (the generic
@@ -214,7 +219,8 @@ int vf_accumulate(int n_dim, int64_t n, const double* w /*[dev]*/, const double*
  */
 int vfp_run_event(int integrand, int n_dim, int n_strat, int64_t n_cubes, int64_t n_events,
                   const int32_t* n_ev /*[dev]*/, const int64_t* ev_offset /*[dev]*/, double xjac,
-                  uint64_t seed, uint32_t iteration, int train, const double* divisions /*[dev]*/,
+                  uint64_t seed, uint32_t iteration, int rng_bits /*52 | 32*/, int train,
+                  const double* divisions /*[dev]*/,
                   const double* xmin /*[host]*/, const double* xdelta /*[host]*/,
                   double* ress /*[dev] [n_cubes]*/, double* ress2 /*[dev] [n_cubes]*/,
                   double* out_hist /*[dev]*/, int accumulate, void* workspace,

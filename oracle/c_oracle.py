@@ -45,6 +45,11 @@ def philox4x32_10(ctr, key):
     return out
 
 
+def set_rng_bits(bits):
+    """Select the engine stream the oracle reproduces: 52 (default) or 32 bits per uniform."""
+    lib().vfo_set_rng_bits(C.c_int(int(bits)))
+
+
 def uniforms(seed, iteration, ev_begin, n, n_dim):
     out = np.empty((n, n_dim), dtype=np.float64)
     lib().vfo_uniforms(C.c_uint64(seed), C.c_uint32(iteration), C.c_uint64(ev_begin), C.c_int64(n),

@@ -74,11 +74,34 @@ static inline double u52_to_uniform(uint32_t hi, uint32_t lo) {
     return fma(v.d, S, C);
 }
 
+/* One word -> uniform in (TECH_CUT, 1-TECH_CUT): top 32 mantissa bits, m = 1 + k*2^-32,
+ *   r = fma(m, S, T - S + S*2^-33) = T + (k + 1/2) * 2^-32 * S     (optional 32-bit stream) */
+static inline double u32_to_uniform(uint32_t k) {
+    union { uint64_t u; double d; } v;
+    v.u = ((uint64_t)(0x3FF00000u | (k >> 12)) << 32) | (uint32_t)(k << 20);
+    const double S = 1.0 - 2.0 * TECH_CUT;
+    const double C = (TECH_CUT - S) + S * 1.1641532182693481e-10; /* 2^-33 */
+    return fma(v.d, S, C);
+}
+
+/* Stream selection: 52 (default, two words per uniform) or 32 (one word per uniform). */
+static int g_rng_bits = 52;
+void vfo_set_rng_bits(int bits) { g_rng_bits = bits == 32 ? 32 : 52; }
+
 /* Uniforms of event `ev` (global index), dims 2p and 2p+1 come from the
  * Philox block with counter (ev_lo, ev_hi, p, iteration), key = seed. */
 static inline void event_uniforms(uint64_t seed, uint32_t iteration, uint64_t ev, int n_dim,
                                   double* r) {
     uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    if (g_rng_bits == 32) { /* block p feeds dims 4p .. 4p+3 */
+        for (int p = 0; 4 * p < n_dim; ++p) {
+            uint32_t ctr[4] = {(uint32_t)ev, (uint32_t)(ev >> 32), (uint32_t)p, iteration};
+            uint32_t o[4];
+            vfo_philox4x32_10(ctr, key, o);
+            for (int h = 0; h < 4 && 4 * p + h < n_dim; ++h) r[4 * p + h] = u32_to_uniform(o[h]);
+        }
+        return;
+    }
     for (int p = 0; 2 * p < n_dim; ++p) {
         uint32_t ctr[4] = {(uint32_t)ev, (uint32_t)(ev >> 32), (uint32_t)p, iteration};
         uint32_t o[4];

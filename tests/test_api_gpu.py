@@ -366,3 +366,15 @@ def test_two_gpu_sharding_matches_single_gpu(tmp_path):
         assert abs(res - data["res"]) <= 1e-9 * abs(res)
         assert abs(err - data["err"]) <= 1e-7 * err
         np.testing.assert_allclose(grid, np.array(data["grid"]), atol=1e-11)
+
+
+@pytest.mark.parametrize("alg", [PlainFlow, VegasFlow, VegasFlowPlus])
+def test_rng_bits_32_option(alg):
+    """rng_bits=32: one Philox word per uniform; same integrals within errors."""
+    inst = alg(4, 200000, verbose=False, rng_bits=32)
+    inst.set_seed(5)
+    inst.compile(vf.integrands.symgauss)
+    res, err = inst.run_integration(4)
+    assert abs(res - 1.0) < 3 * err
+    with pytest.raises(ValueError):
+        alg(4, 1000, rng_bits=24)

@@ -189,3 +189,20 @@ def test_plus_integrates_to_one():
     assert abs(res - 1.0) < 3 * err
     res, err, *_ = R.plus_integrate(R.symgauss, 2, 10000, 4, draw, adaptive=True)
     assert abs(res - 1.0) < 3 * err
+
+
+def test_rng32_stream_definition():
+    """Optional 32-bit stream: (k + 1/2) * 2^-32 mapped into (TECH_CUT, 1-TECH_CUT)."""
+    co.set_rng_bits(32)
+    try:
+        r = co.uniforms(9, 0, 0, 100000, 7)
+        ctr = np.array([5, 0, 1, 0], dtype=np.uint32)
+        words = co.philox4x32_10(ctr, [9, 0])
+        row = co.uniforms(9, 0, 5, 1, 7)[0]
+    finally:
+        co.set_rng_bits(52)
+    assert r.min() > R.TECH_CUT and r.max() < 1 - R.TECH_CUT and abs(r.mean() - 0.5) < 3e-3
+    want = R.TECH_CUT + (words[:3].astype(np.float64) + 0.5) * 2.0**-32 * (1 - 2 * R.TECH_CUT)
+    np.testing.assert_allclose(row[4:7], want, rtol=0, atol=2e-16)  # dims 4..6 <- block 1
+    default = co.uniforms(9, 0, 0, 100, 7)
+    assert not np.array_equal(default, r[:100])

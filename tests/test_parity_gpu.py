@@ -70,10 +70,17 @@ def test_philox_uniforms_bit_exact(lib):
     for d in (1, 2, 3, 8, 20):
         n = 10007
         out = torch.empty((n, d), dtype=torch.float64, device=dev())
-        _lib.check(lib.vf_uniforms(d, 2**33 + 5, n, 0xDEADBEEF12345678, 7, _lib.ptr(out),
-                                   _lib.stream_ptr()))
-        want = co.uniforms(0xDEADBEEF12345678, 7, 2**33 + 5, n, d)
-        np.testing.assert_array_equal(out.cpu().numpy(), want)
+        for bits in (52, 32):
+            _lib.check(lib.vf_uniforms(d, 2**33 + 5, n, 0xDEADBEEF12345678, 7, bits, _lib.ptr(out),
+                                       _lib.stream_ptr()))
+            co.set_rng_bits(bits)
+            try:
+                want = co.uniforms(0xDEADBEEF12345678, 7, 2**33 + 5, n, d)
+            finally:
+                co.set_rng_bits(52)
+            got = out.cpu().numpy()
+            np.testing.assert_array_equal(got, want)
+            assert got.min() > 0.99e-8 and got.max() < 1 - 1e-8
 
 
 @pytest.mark.parametrize("name,d", [("symgauss", 2), ("symgauss", 4), ("symgauss", 8),
@@ -298,7 +305,7 @@ def test_plus_kernel_against_golden(lib, golden):
     ind = torch.empty((n, d), dtype=torch.int32, device=dev())
     wf = torch.empty(n, dtype=torch.float64, device=dev())
     _lib.check(lib.vfp_run_event(0, d, n_strat, n_cubes, n, _lib.ptr(t["n_ev"]), _lib.ptr(t["off"]),
-                                 1.0 / n_cubes, 0, 0, 1, _lib.ptr(t["g"]), None, None,
+                                 1.0 / n_cubes, 0, 0, 52, 1, _lib.ptr(t["g"]), None, None,
                                  _lib.ptr(ress), _lib.ptr(ress2), _lib.ptr(hist), 0, _lib.ptr(ws),
                                  ws.numel() * 8, _lib.ptr(t["r"]), _lib.ptr(x), _lib.ptr(w),
                                  _lib.ptr(ind), _lib.ptr(wf), _lib.stream_ptr()))
@@ -352,7 +359,7 @@ def test_plus_fused_philox_against_oracle(lib):
     ws = torch.zeros(lib.vf_workspace_bytes(d) // 8, dtype=torch.float64, device=dev())
     t_nev, t_off, t_g = to_dev(n_ev), to_dev(off), to_dev(grid)
     _lib.check(lib.vfp_run_event(0, d, n_strat, n_cubes, n, _lib.ptr(t_nev), _lib.ptr(t_off),
-                                 1.0 / n_cubes, 99, 4, 1, _lib.ptr(t_g), None, None, _lib.ptr(ress),
+                                 1.0 / n_cubes, 99, 4, 52, 1, _lib.ptr(t_g), None, None, _lib.ptr(ress),
                                  _lib.ptr(ress2), _lib.ptr(hist), 0, _lib.ptr(ws), ws.numel() * 8,
                                  None, None, None, None, None, _lib.stream_ptr()))
     torch.cuda.synchronize()
@@ -452,3 +459,37 @@ def test_kernel_timing_hook(lib):
     _lib.check(lib.vf_kernel_time_ms(ctypes.byref(tot), ctypes.byref(cnt)))
     lib.vf_kernel_timing(0)
     assert cnt.value == 3 and 0.0 < tot.value < 50.0
+
+
+def test_rng32_stream_fused_kernel_against_oracle(lib):
+    """Optional 32-bit stream (VF_MODE_RNG32): four uniforms per Philox block.  Same parity
+    bars as the default stream, against the oracle switched to the same stream definition."""
+    n, seed, it = 200000, 424242, 2
+    co.set_rng_bits(32)
+    try:
+        for name, d in (("symgauss", 8), ("product", 5), ("symgauss", 3)):
+            rng = np.random.default_rng(d)
+            grid = np.sort(rng.random((d, 51)), axis=1) * 0.5 + np.linspace(0, 0.5, 51)
+            grid[:, 0], grid[:, -1] = 0.0, 1.0
+            iid = lib.vf_integrand_id(name.encode())
+            s1, s2, hist = gpu_run_event(lib, 1 | _lib.MODE_RNG32, iid, d, 77, n, 1.0 / n, seed, it,
+                                         True, grid)
+            o1, o2, ohist = co.run_event(co.MODE_VEGAS, name, d, 77, n, 1.0 / n, seed, it, True, grid)
+            assert abs(s1 - o1) <= 1e-11 * abs(o1) and abs(s2 - o2) <= 1e-11 * abs(o2)
+            np.testing.assert_allclose(hist, ohist, rtol=1e-10, atol=1e-300)
+            # and it is a different stream from the default one
+            d1, _, _ = gpu_run_event(lib, 1, iid, d, 77, n, 1.0 / n, seed, it, True, grid)
+            assert d1 != s1
+        # unfused sampler on the 32-bit stream
+        d = 6
+        grid = R.initial_divisions(d)
+        x = torch.empty((1000, d), dtype=torch.float64, device=dev())
+        w = torch.empty(1000, dtype=torch.float64, device=dev())
+        _lib.check(lib.vf_sample(1 | _lib.MODE_RNG32, d, 5, 1000, 1e-3, seed, 1, _lib.ptr(to_dev(grid)),
+                                 None, None, _lib.ptr(x), _lib.ptr(w), None, _lib.stream_ptr()))
+        r = co.uniforms(seed, 1, 5, 1000, d)
+        xo, wo, _, _ = co.digest_from_uniforms(co.MODE_VEGAS, "product", r, grid, 1e-3)
+        np.testing.assert_array_equal(x.cpu().numpy(), xo)
+        np.testing.assert_array_equal(w.cpu().numpy(), wo)
+    finally:
+        co.set_rng_bits(52)

@@ -12,6 +12,7 @@ SO_PATH = os.path.join(_HERE, "lib", "libvegasflow_b200.so")
 
 MODE_PLAIN = 0
 MODE_VEGAS = 1
+MODE_RNG32 = 0x100  # OR'ed into a mode word: 4 x 32-bit uniforms per Philox block
 
 _P = C.c_void_p
 _SIGNATURES = {
@@ -36,13 +37,15 @@ _SIGNATURES = {
     "vf_iteration_epilogue": (C.c_int, [C.c_int, C.c_int64, C.c_int, _P, _P, _P, _P, _P]),
     "vf_digest_from_uniforms": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, _P, _P, C.c_double,
                                           _P, _P, _P, _P, _P, _P, _P]),
-    "vf_uniforms": (C.c_int, [C.c_int, C.c_uint64, C.c_int64, C.c_uint64, C.c_uint32, _P, _P]),
+    "vf_uniforms": (C.c_int, [C.c_int, C.c_uint64, C.c_int64, C.c_uint64, C.c_uint32, C.c_int, _P,
+                              _P]),
     "vf_sample": (C.c_int, [C.c_int, C.c_int, C.c_uint64, C.c_int64, C.c_double, C.c_uint64,
                             C.c_uint32, _P, _P, _P, _P, _P, _P, _P]),
     "vf_accumulate": (C.c_int, [C.c_int, C.c_int64, _P, _P, _P, C.c_int, _P, _P, C.c_int, _P,
                                 C.c_size_t, _P]),
     "vfp_run_event": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, _P, _P,
-                                C.c_double, C.c_uint64, C.c_uint32, C.c_int, _P, _P, _P, _P, _P,
+                                C.c_double, C.c_uint64, C.c_uint32, C.c_int, C.c_int, _P, _P, _P,
+                                _P, _P,
                                 _P, C.c_int, _P, C.c_size_t, _P, _P, _P, _P, _P, _P]),
     "vfp_iteration_epilogue": (C.c_int, [C.c_int64, _P, _P, C.c_int, C.c_int, C.c_int64, _P, _P,
                                          _P, _P, _P, _P]),

@@ -103,6 +103,18 @@ static size_t workspace_need(int n_dim) {
     return ws_doubles(n_dim) * sizeof(double);
 }
 
+// `mode` words carry the sampling mode in the low byte and stream options above it.
+static inline int split_mode(int& mode) {
+    const int rng_bits = (mode & VF_MODE_RNG32) ? 32 : 52;
+    mode &= 0xff;
+    return rng_bits;
+}
+static inline int check_rng_bits(int rng_bits) {
+    if (rng_bits == 52 || rng_bits == 32) return VF_OK;
+    set_error("rng_bits must be 52 or 32 (got %d)", rng_bits);
+    return VF_ERR_INVALID;
+}
+
 static int check_common(int n_dim, int64_t n) {
     if (n_dim < 1) {
         set_error("n_dim must be >= 1 (got %d)", n_dim);
@@ -180,6 +192,7 @@ int vf_run_event(int mode, int integrand, int n_dim, uint64_t ev_begin, int64_t 
                  size_t workspace_bytes, void* stream) {
     int rc = check_common(n_dim, n_events);
     if (rc) return rc;
+    const int rng_bits = split_mode(mode);
     if (mode != VF_MODE_PLAIN && mode != VF_MODE_VEGAS) {
         set_error("unknown mode %d", mode);
         return VF_ERR_INVALID;
@@ -199,6 +212,7 @@ int vf_run_event(int mode, int integrand, int n_dim, uint64_t ev_begin, int64_t 
     }
     EventLaunch L;
     L.mode = mode;
+    L.rng_bits = rng_bits;
     L.n_dim = n_dim;
     L.stream = (cudaStream_t)stream;
     int nblocks = 0;
@@ -226,6 +240,7 @@ int vf_run_iterations(int mode, int integrand, int n_dim, int64_t n_events, uint
                       void* workspace, size_t workspace_bytes, void* stream) {
     int rc = check_common(n_dim, n_events);
     if (rc) return rc;
+    const int rng_bits = split_mode(mode);
     if (mode != VF_MODE_PLAIN && mode != VF_MODE_VEGAS) {
         set_error("unknown mode %d", mode);
         return VF_ERR_INVALID;
@@ -242,6 +257,7 @@ int vf_run_iterations(int mode, int integrand, int n_dim, int64_t n_events, uint
     const bool with_hist = mode == VF_MODE_VEGAS && train;
     EventLaunch L;
     L.mode = mode;
+    L.rng_bits = rng_bits;
     L.n_dim = n_dim;
     L.stream = (cudaStream_t)stream;
     int nblocks = 0;
@@ -286,6 +302,7 @@ int vf_run_iterations_sharded(int mode, int integrand, int n_dim, uint64_t ev_be
     const uint64_t seq = first_seq;
     int rc = check_common(n_dim, n_events_local);
     if (rc) return rc;
+    const int rng_bits = split_mode(mode);
     if (mode != VF_MODE_PLAIN && mode != VF_MODE_VEGAS) {
         set_error("unknown mode %d", mode);
         return VF_ERR_INVALID;
@@ -303,6 +320,7 @@ int vf_run_iterations_sharded(int mode, int integrand, int n_dim, uint64_t ev_be
     const bool with_hist = mode == VF_MODE_VEGAS && train;
     EventLaunch L;
     L.mode = mode;
+    L.rng_bits = rng_bits;
     L.n_dim = n_dim;
     L.stream = (cudaStream_t)stream;
     int nblocks = 0;
@@ -383,10 +401,13 @@ int vf_digest_from_uniforms(int mode, int integrand, int n_dim, int64_t n, const
 }
 
 int vf_uniforms(int n_dim, uint64_t ev_begin, int64_t n, uint64_t seed, uint32_t iteration,
-                double* rnds, void* stream) {
+                int rng_bits, double* rnds, void* stream) {
     int rc = check_common(n_dim, n);
     if (rc) return rc;
-    return launch_uniforms(n_dim, ev_begin, n, seed, iteration, rnds, (cudaStream_t)stream);
+    rc = check_rng_bits(rng_bits);
+    if (rc) return rc;
+    return launch_uniforms(n_dim, ev_begin, n, seed, iteration, rng_bits, rnds,
+                           (cudaStream_t)stream);
 }
 
 int vf_sample(int mode, int n_dim, uint64_t ev_begin, int64_t n, double xjac, uint64_t seed,
@@ -394,6 +415,7 @@ int vf_sample(int mode, int n_dim, uint64_t ev_begin, int64_t n, double xjac, ui
               const double* xdelta, double* x, double* w, int32_t* ind, void* stream) {
     int rc = check_common(n_dim, n);
     if (rc) return rc;
+    const int rng_bits = split_mode(mode);
     if (n_dim > kMaxDim) {
         set_error("vf_sample supports n_dim <= %d", kMaxDim);
         return VF_ERR_UNSUPPORTED;
@@ -405,8 +427,8 @@ int vf_sample(int mode, int n_dim, uint64_t ev_begin, int64_t n, double xjac, ui
     Limits lim;
     rc = make_limits(n_dim, xmin, xdelta, &lim);
     if (rc) return rc;
-    return launch_sample(mode, n_dim, ev_begin, n, xjac, seed, iteration, divisions, lim, x, w, ind,
-                         (cudaStream_t)stream);
+    return launch_sample(mode, n_dim, ev_begin, n, xjac, seed, iteration, rng_bits, divisions, lim,
+                         x, w, ind, (cudaStream_t)stream);
 }
 
 int vf_accumulate(int n_dim, int64_t n, const double* w, const double* f, const int32_t* ind,
@@ -437,11 +459,14 @@ int vf_accumulate(int n_dim, int64_t n, const double* w, const double* f, const 
 
 int vfp_run_event(int integrand, int n_dim, int n_strat, int64_t n_cubes, int64_t n_events,
                   const int32_t* n_ev, const int64_t* ev_offset, double xjac, uint64_t seed,
-                  uint32_t iteration, int train, const double* divisions, const double* xmin,
+                  uint32_t iteration, int rng_bits, int train, const double* divisions,
+                  const double* xmin,
                   const double* xdelta, double* ress, double* ress2, double* out_hist,
                   int accumulate, void* workspace, size_t workspace_bytes, const double* rnds,
                   double* x, double* w, int32_t* ind, double* wf, void* stream) {
     int rc = check_common(n_dim, n_events);
+    if (rc) return rc;
+    rc = check_rng_bits(rng_bits);
     if (rc) return rc;
     if (!n_ev || !ev_offset || !divisions || !ress || !ress2 || !workspace ||
         (train && !out_hist) || n_strat < 1 || n_cubes < 1) {
@@ -454,6 +479,7 @@ int vfp_run_event(int integrand, int n_dim, int n_strat, int64_t n_cubes, int64_
     }
     PlusLaunch L;
     L.n_dim = n_dim;
+    L.rng_bits = rng_bits;
     L.stream = (cudaStream_t)stream;
     int nblocks = 0;
     L.nblocks_out = &nblocks;

@@ -399,25 +399,27 @@ int launch_epilogue(int n_dim, int64_t n_events, int train, const double* sums, 
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) uniforms_kernel(int n_dim, uint64_t ev_begin, int64_t n,
                                                        const __grid_constant__ PhiloxKeys pk,
-                                                       uint32_t iteration, double* rnds) {
+                                                       uint32_t iteration, int rng_bits,
+                                                       double* rnds) {
+    const int pc = rng_bits == 32 ? 4 : 2;  // uniforms per Philox block
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x) {
         const uint64_t e = ev_begin + (uint64_t)i;
-        for (int p = 0; 2 * p < n_dim; ++p) {
+        for (int p = 0; pc * p < n_dim; ++p) {
             const uint4 o = philox4x32_10((uint32_t)e, (uint32_t)(e >> 32), (uint32_t)p, iteration,
                                           pk);
-            rnds[i * n_dim + 2 * p] = u52_to_uniform(o.x, o.y);
-            if (2 * p + 1 < n_dim) rnds[i * n_dim + 2 * p + 1] = u52_to_uniform(o.z, o.w);
+            for (int h = 0; h < pc && pc * p + h < n_dim; ++h)
+                rnds[i * n_dim + pc * p + h] = rng_uniform(o, h, rng_bits);
         }
     }
 }
 
 int launch_uniforms(int n_dim, uint64_t ev_begin, int64_t n, uint64_t seed, uint32_t iteration,
-                    double* rnds, cudaStream_t stream) {
+                    int rng_bits, double* rnds, cudaStream_t stream) {
     if (n <= 0) return VF_OK;
     const int blocks = (int)imin64((n + 255) / 256, (int64_t)sm_count() * 8);
     uniforms_kernel<<<blocks, 256, 0, stream>>>(n_dim, ev_begin, n, make_philox_keys(seed),
-                                                iteration, rnds);
+                                                iteration, rng_bits, rnds);
     count_launch();
     VF_CUDA_CHECK(cudaGetLastError());
     return VF_OK;
@@ -430,7 +432,7 @@ int launch_uniforms(int n_dim, uint64_t ev_begin, int64_t n, uint64_t seed, uint
 __global__ void __launch_bounds__(256) sample_kernel(int mode, int n_dim, uint64_t ev_begin,
                                                      int64_t n, double xjac,
                                                      const __grid_constant__ PhiloxKeys pk,
-                                                     uint32_t iteration,
+                                                     uint32_t iteration, int rng_bits,
                                                      const double* __restrict__ divisions,
                                                      const __grid_constant__ Limits lim, double* x,
                                                      double* w, int32_t* ind) {
@@ -448,13 +450,14 @@ __global__ void __launch_bounds__(256) sample_kernel(int mode, int n_dim, uint64
          i += (int64_t)gridDim.x * blockDim.x) {
         const uint64_t e = ev_begin + (uint64_t)i;
         double wt = 1.0;
-        for (int p = 0; 2 * p < n_dim; ++p) {
+        const int pc = rng_bits == 32 ? 4 : 2;
+        for (int p = 0; pc * p < n_dim; ++p) {
             const uint4 o = philox4x32_10((uint32_t)e, (uint32_t)(e >> 32), (uint32_t)p, iteration,
                                           pk);
-            for (int h = 0; h < 2; ++h) {
-                const int j = 2 * p + h;
+            for (int h = 0; h < pc; ++h) {
+                const int j = pc * p + h;
                 if (j >= n_dim) break;
-                const double r = h == 0 ? u52_to_uniform(o.x, o.y) : u52_to_uniform(o.z, o.w);
+                const double r = rng_uniform(o, h, rng_bits);
                 double xv;
                 int bin = 0;
                 if (mode == VF_MODE_VEGAS) {
@@ -478,14 +481,15 @@ __global__ void __launch_bounds__(256) sample_kernel(int mode, int n_dim, uint64
 }
 
 int launch_sample(int mode, int n_dim, uint64_t ev_begin, int64_t n, double xjac, uint64_t seed,
-                  uint32_t iteration, const double* divisions, const Limits& lim, double* x,
+                  uint32_t iteration, int rng_bits, const double* divisions, const Limits& lim,
+                  double* x,
                   double* w, int32_t* ind, cudaStream_t stream) {
     if (n <= 0) return VF_OK;
     const int blocks = (int)imin64((n + 255) / 256, (int64_t)sm_count() * 8);
     const size_t smem = mode == VF_MODE_VEGAS ? (size_t)n_dim * kBins * 16 : 0;
     sample_kernel<<<blocks, 256, smem, stream>>>(mode, n_dim, ev_begin, n, xjac,
-                                                 make_philox_keys(seed), iteration, divisions, lim,
-                                                 x, w, ind);
+                                                 make_philox_keys(seed), iteration, rng_bits,
+                                                 divisions, lim, x, w, ind);
     count_launch();
     VF_CUDA_CHECK(cudaGetLastError());
     return VF_OK;

@@ -23,10 +23,10 @@ int launch_refine(int n_dim, const double* hist, double* divisions, cudaStream_t
 int launch_epilogue(int n_dim, int64_t n_events, int train, const double* sums, const double* hist,
                     double* divisions, double* result, cudaStream_t stream);
 int launch_uniforms(int n_dim, uint64_t ev_begin, int64_t n, uint64_t seed, uint32_t iteration,
-                    double* rnds, cudaStream_t stream);
+                    int rng_bits, double* rnds, cudaStream_t stream);
 int launch_sample(int mode, int n_dim, uint64_t ev_begin, int64_t n, double xjac, uint64_t seed,
-                  uint32_t iteration, const double* divisions, const Limits& lim, double* x,
-                  double* w, int32_t* ind, cudaStream_t stream);
+                  uint32_t iteration, int rng_bits, const double* divisions, const Limits& lim,
+                  double* x, double* w, int32_t* ind, cudaStream_t stream);
 int launch_accumulate(int n_dim, int64_t n, const double* w, const double* f, const int32_t* ind,
                       int do_hist, double* partials, int* nblocks_out, cudaStream_t stream);
 int launch_plus_epilogue(int64_t n_cubes, const double* ress, const double* ress2, int adaptive,

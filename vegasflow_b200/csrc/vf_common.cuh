@@ -99,6 +99,31 @@ __device__ __forceinline__ double u52_to_uniform(uint32_t hi, uint32_t lo) {
     return fma(m, S, C);
 }
 
+// One 32-bit word -> uniform double in (TECH_CUT, 1-TECH_CUT): the word fills the TOP 32
+// mantissa bits, m = 1 + k*2^-32, r = fma(m, S, T - S + S*2^-33) = T + (k + 1/2)*2^-32*S.
+// Optional stream (rng_bits = 32): four uniforms per Philox block instead of two, i.e. half the
+// integer-multiply work; resolution 2.3e-10 (TECH_CUT is 1e-8).  Not the default.
+__device__ __forceinline__ double u32_to_uniform(uint32_t k) {
+    const double m = __hiloint2double((int)(0x3FF00000u | (k >> 12)), (int)(k << 20));
+    constexpr double S = 1.0 - 2.0 * kTechCut;
+    constexpr double C = (kTechCut - S) + S * 1.1641532182693481e-10;  // 2^-33
+    return fma(m, S, C);
+}
+
+// Uniforms per Philox block and word selection for the two stream definitions.
+template <int RB>
+struct Rng {
+    static_assert(RB == 52 || RB == 32, "rng_bits is 52 or 32");
+    static constexpr int kPerCall = RB == 32 ? 4 : 2;
+    static __device__ __forceinline__ double uniform(const uint4& o, int h) {
+        if (RB == 32) return u32_to_uniform(h == 0 ? o.x : (h == 1 ? o.y : (h == 2 ? o.z : o.w)));
+        return h == 0 ? u52_to_uniform(o.x, o.y) : u52_to_uniform(o.z, o.w);
+    }
+};
+__device__ __forceinline__ double rng_uniform(const uint4& o, int h, int rng_bits) {
+    return rng_bits == 32 ? Rng<32>::uniform(o, h) : Rng<52>::uniform(o, h);
+}
+
 // ---- VEGAS map, one dimension ----------------------------------------------
 // vflow.py:117 (xn = 50*(1-r)), :67 (ind = trunc), :70-76 (x), :78 (Delta*50).
 // `tbl` points at the (x_ini, Delta) pairs of this dimension in shared memory,

@@ -146,7 +146,7 @@ __device__ __forceinline__ void hist_update(char* hist_lane, const int (&bin)[ND
 // K1: fused event kernel (VegasFlow._run_event, vflow.py:389-430; PlainFlow
 // plain.py:18-35).  Thread t evaluates global events ev_begin + t, + stride...
 // ---------------------------------------------------------------------------
-template <class I, int NDIM, int MODE>
+template <class I, int NDIM, int MODE, int RB>
 __global__ void __launch_bounds__(Cfg<NDIM>::kThreads, min_blocks<I, NDIM>())
 event_kernel(const __grid_constant__ EventKernelArgs a) {
     using C = Cfg<NDIM>;
@@ -168,15 +168,16 @@ event_kernel(const __grid_constant__ EventKernelArgs a) {
         double x[NDIM];
         int bin[NDIM];
         double w = 1.0;
+        constexpr int PC = Rng<RB>::kPerCall;  // uniforms per Philox block
 #pragma unroll
-        for (int p = 0; p < (NDIM + 1) / 2; ++p) {
+        for (int p = 0; p < (NDIM + PC - 1) / PC; ++p) {
             const uint4 o = philox4x32_10((uint32_t)n, (uint32_t)(n >> 32), (uint32_t)p,
                                           a.iteration, a.pk);
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int j = 2 * p + h;
+            for (int h = 0; h < PC; ++h) {
+                const int j = PC * p + h;
                 if (j < NDIM) {
-                    const double r = h == 0 ? u52_to_uniform(o.x, o.y) : u52_to_uniform(o.z, o.w);
+                    const double r = Rng<RB>::uniform(o, h);
                     if (MODE == VF_MODE_VEGAS) {
                         const double xn = __dmul_rn(kFBins, __dsub_rn(1.0, r));  // vflow.py:117
                         double wfac;
@@ -287,7 +288,7 @@ struct PlusKernelArgs {
     IntegrandConsts ic;
 };
 
-template <class I, int NDIM, bool EXT>
+template <class I, int NDIM, bool EXT, int RB>
 __global__ void __launch_bounds__(Cfg<NDIM>::kThreads, plus_min_blocks<I, NDIM>())
 plus_event_kernel(const __grid_constant__ PlusKernelArgs a) {
     using C = Cfg<NDIM>;
@@ -339,19 +340,20 @@ plus_event_kernel(const __grid_constant__ PlusKernelArgs a) {
         double x[NDIM];
         int bin[NDIM];
         double w = 1.0;
+        constexpr int PC = Rng<RB>::kPerCall;
 #pragma unroll
-        for (int p = 0; p < (NDIM + 1) / 2; ++p) {
+        for (int p = 0; p < (NDIM + PC - 1) / PC; ++p) {
             uint4 o;
             if (!EXT)
                 o = philox4x32_10((uint32_t)e, (uint32_t)((uint64_t)e >> 32), (uint32_t)p,
                                   a.iteration, a.pk);
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int j = 2 * p + h;
+            for (int h = 0; h < PC; ++h) {
+                const int j = PC * p + h;
                 if (j < NDIM) {
                     double r;
                     if (EXT) r = a.rnds[e * NDIM + j];
-                    else r = h == 0 ? u52_to_uniform(o.x, o.y) : u52_to_uniform(o.z, o.w);
+                    else r = Rng<RB>::uniform(o, h);
                     // vflowplus.py:72: (points + rnds) * FBINS / n_strat
                     const double xn =
                         div_rn_by(__dmul_rn(__dadd_rn(coords[j], r), kFBins), fstrat, rstrat);
@@ -392,6 +394,7 @@ plus_event_kernel(const __grid_constant__ PlusKernelArgs a) {
 // ---------------------------------------------------------------------------
 struct EventLaunch {
     int mode, n_dim;
+    int rng_bits = 52;
     EventKernelArgs k;
     cudaStream_t stream;
     int* nblocks_out;
@@ -403,6 +406,7 @@ struct DigestLaunch {
 };
 struct PlusLaunch {
     int n_dim;
+    int rng_bits = 52;
     PlusKernelArgs k;
     cudaStream_t stream;
     int* nblocks_out;
@@ -426,10 +430,10 @@ inline int grid_blocks_for(int64_t n_events, int threads, int min_blocks_per_sm)
     return (int)want;
 }
 
-template <class I, int NDIM, int MODE>
+template <class I, int NDIM, int MODE, int RB>
 int launch_event_dim(const EventLaunch& L) {
     using C = Cfg<NDIM>;
-    auto kern = event_kernel<I, NDIM, MODE>;
+    auto kern = event_kernel<I, NDIM, MODE, RB>;
     const size_t smem = MODE == VF_MODE_VEGAS ? C::kSmemBytes : 0;
     static bool configured = false;
     if (!configured) {
@@ -469,7 +473,9 @@ template <class I, int NDIM>
 int launch_plus_dim(const PlusLaunch& L) {
     using C = Cfg<NDIM>;
     const bool ext = L.k.rnds != nullptr;
-    auto kern = ext ? plus_event_kernel<I, NDIM, true> : plus_event_kernel<I, NDIM, false>;
+    auto kern = ext ? plus_event_kernel<I, NDIM, true, 52>
+                    : (L.rng_bits == 32 ? plus_event_kernel<I, NDIM, false, 32>
+                                        : plus_event_kernel<I, NDIM, false, 52>);
     VF_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)C::kSmemBytes));
     const int blocks = grid_blocks_for(L.k.n_events, C::kThreads, plus_min_blocks<I, NDIM>());
@@ -485,8 +491,11 @@ int launch_plus_dim(const PlusLaunch& L) {
 // Instantiates launch_event/launch_digest/launch_plus/supported_dim for integrand I.
 #define VF_DIM_CASE_EVENT(D)                                                              \
     case D:                                                                               \
-        return L.mode == VF_MODE_VEGAS ? launch_event_dim<I, D, VF_MODE_VEGAS>(L)         \
-                                       : launch_event_dim<I, D, VF_MODE_PLAIN>(L);
+        if (L.rng_bits == 32)                                                             \
+            return L.mode == VF_MODE_VEGAS ? launch_event_dim<I, D, VF_MODE_VEGAS, 32>(L) \
+                                           : launch_event_dim<I, D, VF_MODE_PLAIN, 32>(L); \
+        return L.mode == VF_MODE_VEGAS ? launch_event_dim<I, D, VF_MODE_VEGAS, 52>(L)     \
+                                       : launch_event_dim<I, D, VF_MODE_PLAIN, 52>(L);
 #define VF_DIM_CASE_DIGEST(D)                                                             \
     case D:                                                                               \
         return L.mode == VF_MODE_VEGAS ? launch_digest_dim<I, D, VF_MODE_VEGAS>(L)        \

@@ -65,6 +65,7 @@ class MonteCarloFlow(ABC):
             iteration in one launch regardless of this value.
         `list_devices`: accepted for compatibility; one process drives one GPU
         `xmin`, `xmax`: integration limits
+        `rng_bits`: 52 (default) or 32 bits of Philox output per uniform draw
     """
 
     _CAN_RUN_VECTORIAL = False
@@ -81,6 +82,7 @@ class MonteCarloFlow(ABC):
         verbose=True,
         xmin=None,
         xmax=None,
+        rng_bits=None,
         **kwargs,
     ):
         if "simplify_signature" in kwargs:
@@ -124,7 +126,14 @@ class MonteCarloFlow(ABC):
         self._xmin_c = _lib.host_doubles(self._xmin)
         self._xdelta_c = _lib.host_doubles(self._xdelta)
 
-        # Random stream: Philox key + iteration counter
+        # Random stream.  rng_bits = 52 (default): two Philox words per uniform, all 52 mantissa
+        # bits like tf.random.uniform; 32: one word per uniform (half the integer work).
+        if rng_bits is None:
+            rng_bits = int(os.environ.get("VEGASFLOW_B200_RNG_BITS", "52"))
+        if rng_bits not in (52, 32):
+            raise ValueError(f"rng_bits must be 52 or 32, got {rng_bits}")
+        self._rng_bits = rng_bits
+        # Philox key + iteration counter
         self._seed = (_BASE_SEED + next(_instance_counter)) & 0xFFFFFFFFFFFFFFFF
         self._iteration = 0
         # Device state is allocated lazily (construction works without a GPU so
@@ -191,7 +200,7 @@ class MonteCarloFlow(ABC):
         xchg.seq += n_iter
         _lib.check(
             lib.vf_run_iterations_sharded(
-                self._MODE, self._builtin.integrand_id(), self.n_dim, begin, end - begin,
+                self._mode_word, self._builtin.integrand_id(), self.n_dim, begin, end - begin,
                 self.n_events, self._seed, self._iteration, n_iter,
                 int(bool(getattr(self, "train", False))), _lib.ptr(self._grid_tensor()),
                 self._xmin_c, self._xdelta_c, _lib.ptr(self._packed), _lib.ptr(rows),
@@ -221,7 +230,7 @@ class MonteCarloFlow(ABC):
         rows = self._result_rows(n_iter)
         _lib.check(
             lib.vf_run_iterations(
-                self._MODE, self._builtin.integrand_id(), self.n_dim, self.n_events, self._seed,
+                self._mode_word, self._builtin.integrand_id(), self.n_dim, self.n_events, self._seed,
                 self._iteration, n_iter, int(bool(getattr(self, "train", False))),
                 _lib.ptr(self._grid_tensor()), self._xmin_c, self._xdelta_c,
                 _lib.ptr(self._packed), _lib.ptr(rows), _lib.ptr(self._workspace),
@@ -230,6 +239,11 @@ class MonteCarloFlow(ABC):
         )
         self._iteration += n_iter
         return rows
+
+    @property
+    def _mode_word(self):
+        """Sampling mode plus stream options, as the C ABI's `mode` argument."""
+        return self._MODE | (_lib.MODE_RNG32 if self._rng_bits == 32 else 0)
 
     @property
     def _hist(self):
@@ -296,7 +310,7 @@ class MonteCarloFlow(ABC):
             ind = torch.empty((n, self.n_dim), dtype=torch.int32, device=self._device)
         _lib.check(
             lib.vf_sample(
-                self._MODE, self.n_dim, ev_begin, n, self.xjac, self._seed, self._iteration,
+                self._mode_word, self.n_dim, ev_begin, n, self.xjac, self._seed, self._iteration,
                 _lib.ptr(self._grid_tensor()), self._xmin_c, self._xdelta_c, _lib.ptr(x),
                 _lib.ptr(w), _lib.ptr(ind), _lib.stream_ptr(),
             )

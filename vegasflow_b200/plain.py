@@ -29,7 +29,7 @@ class PlainFlow(MonteCarloFlow):
         if isinstance(integrand, BuiltinIntegrand):
             _lib.check(
                 lib.vf_run_event(
-                    self._MODE, integrand.integrand_id(), self.n_dim, ev_begin, n_events,
+                    self._mode_word, integrand.integrand_id(), self.n_dim, ev_begin, n_events,
                     self.xjac, self._seed, self._iteration, 0, None, self._xmin_c,
                     self._xdelta_c, _lib.ptr(self._sums), None, accumulate,
                     _lib.ptr(self._workspace), self._workspace.numel() * 8, _lib.stream_ptr(),

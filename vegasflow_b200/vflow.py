@@ -166,7 +166,7 @@ class VegasFlow(MonteCarloFlow):
         if isinstance(integrand, BuiltinIntegrand):
             _lib.check(
                 lib.vf_run_event(
-                    self._MODE, integrand.integrand_id(), self.n_dim, ev_begin, n_events,
+                    self._mode_word, integrand.integrand_id(), self.n_dim, ev_begin, n_events,
                     self.xjac, self._seed, self._iteration, int(bool(self.train)),
                     _lib.ptr(grid), self._xmin_c, self._xdelta_c, _lib.ptr(self._sums),
                     _lib.ptr(self._hist), accumulate, _lib.ptr(self._workspace),

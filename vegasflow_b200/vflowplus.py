@@ -137,8 +137,8 @@ class VegasFlowPlus(VegasFlow):
         for _ in range(n_events // self.n_events + 1):
             n = self.n_events
             u = torch.empty((n, self.n_dim), dtype=DTYPE, device=self._device)
-            _lib.check(lib.vf_uniforms(self.n_dim, 0, n, self._seed, self._iteration, _lib.ptr(u),
-                                       _lib.stream_ptr()))
+            _lib.check(lib.vf_uniforms(self.n_dim, 0, n, self._seed, self._iteration,
+                                       self._rng_bits, _lib.ptr(u), _lib.stream_ptr()))
             self._iteration += 1
             x = torch.empty((n, self.n_dim), dtype=DTYPE, device=self._device)
             w = torch.empty((n,), dtype=DTYPE, device=self._device)
@@ -170,7 +170,8 @@ class VegasFlowPlus(VegasFlow):
             lib.vfp_run_event(
                 integrand.integrand_id(), self.n_dim, self._n_strat, self._n_cubes, int(n_events),
                 _lib.ptr(st["n_ev"]), _lib.ptr(st["ev_offset"]), self.xjac, self._seed,
-                self._iteration, int(bool(train)), _lib.ptr(self._grid_tensor()), self._xmin_c,
+                self._iteration, self._rng_bits, int(bool(train)), _lib.ptr(self._grid_tensor()),
+                self._xmin_c,
                 self._xdelta_c, _lib.ptr(ress), _lib.ptr(ress2), _lib.ptr(self._hist), 0,
                 _lib.ptr(self._workspace), self._workspace.numel() * 8, _lib.ptr(rnds),
                 _lib.ptr(x), _lib.ptr(w), _lib.ptr(ind), _lib.ptr(wf), _lib.stream_ptr(),
@@ -195,8 +196,8 @@ class VegasFlowPlus(VegasFlow):
         lib = _lib.load()
         n = self.n_events
         u = torch.empty((n, self.n_dim), dtype=DTYPE, device=self._device)
-        _lib.check(lib.vf_uniforms(self.n_dim, 0, n, self._seed, self._iteration, _lib.ptr(u),
-                                   _lib.stream_ptr()))
+        _lib.check(lib.vf_uniforms(self.n_dim, 0, n, self._seed, self._iteration, self._rng_bits,
+                                   _lib.ptr(u), _lib.stream_ptr()))
         x = torch.empty((n, self.n_dim), dtype=DTYPE, device=self._device)
         w = torch.empty((n,), dtype=DTYPE, device=self._device)
         ind = torch.empty((n, self.n_dim), dtype=torch.int32, device=self._device)
