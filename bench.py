@@ -255,7 +255,6 @@ def main():
     _lib.check(lib.vf_fp64_peak_probe(20000, ctypes.byref(peak)))
 
     inst = make_instance(wl, world)
-    n_step_total = inst.n_events  # whole-job events per step (all ranks)
 
     def run_n(n):
         """n steps of the product path (identical count on every rank)."""
@@ -293,7 +292,6 @@ def main():
     sampler = ClockSampler(torch.cuda.current_device())
     ev0 = torch.cuda.Event(enable_timing=True)
     ev1 = torch.cuda.Event(enable_timing=True)
-    events_done = 0
     def run_steps():
         return run_n(K)
 

@@ -206,3 +206,18 @@ def test_rng32_stream_definition():
     np.testing.assert_allclose(row[4:7], want, rtol=0, atol=2e-16)  # dims 4..6 <- block 1
     default = co.uniforms(9, 0, 0, 100, 7)
     assert not np.array_equal(default, r[:100])
+
+
+def test_flop_counts_match_the_abi_table():
+    """F_alg of the matrix-element integrands is counted, not guessed: the op-counting ndarray
+    of oracle/count_flops.py on the numpy restatement must agree with vf_flops_per_event."""
+    from oracle.count_flops import count
+    from vegasflow_b200 import _lib
+
+    lib = _lib.load()
+    for name, d in (("symgauss", 4), ("symgauss", 8), ("product", 8), ("drellyan_lo", 4),
+                    ("singletop_lo", 3)):
+        flops, _ = count(R.INTEGRANDS[name], d)
+        abi = lib.vf_flops_per_event(1, lib.vf_integrand_id(name.encode()), d, 0) - (12 * d + 5)
+        # symgauss: SURVEY counts d adds for the reduce_sum, the restatement starts from term 0
+        assert abs(abi - flops) <= 1, (name, d, abi, flops)

@@ -177,8 +177,11 @@ double vf_flops_per_event(int mode, int integrand, int n_dim, int plus) {
     switch (integrand) {
         case VF_INTEGRAND_SYMGAUSS: return base + 4.0 * d + 4.0;
         case VF_INTEGRAND_PRODUCT: return base + (d - 1.0);
-        case VF_INTEGRAND_DRELLYAN_LO: return base + 560.0;   // hand count, DESIGN.md
-        case VF_INTEGRAND_SINGLETOP_LO: return base + 900.0;  // hand count, DESIGN.md
+        // counted on the numpy restatement of the reference bodies with an op-counting ndarray
+        // (oracle/count_flops.py): operations on non-zero terms only -- the products/sums the
+        // reference forms with exact complex zeros (another 465 / 1421) are not credited
+        case VF_INTEGRAND_DRELLYAN_LO: return base + 448.0;
+        case VF_INTEGRAND_SINGLETOP_LO: return base + 1354.0;
         default: return base;
     }
 }

@@ -95,7 +95,7 @@ __device__ long long g_phase_clock[16];
 
 __device__ void refine_dimension(const double* __restrict__ t_res_sq, double* sub_global) {
     __shared__ double sub[kEdges], sm[kBins], wei[kBins];
-    __shared__ double s_sum, s_ave;
+    __shared__ double s_sum;
     __shared__ double b_cur[kBins], b_prev[kBins], b_bw[kBins];
     __shared__ int b_n[kBins];
     const int i = threadIdx.x;
@@ -135,7 +135,6 @@ __device__ void refine_dimension(const double* __restrict__ t_res_sq, double* su
         double s = 0.0;
         for (int k = 0; k < kBins; ++k) s = __dadd_rn(s, wei[k]);
         const double ave = __ddiv_rn(s, (double)kBins);  // :166
-        s_ave = ave;
         VF_PHASE(6);
         // serial scan :195-205 (state: bin_weight, n_bin, cur, prev).  The reference advances
         // n while bin_weight < ave and then emits one boundary; here the same sequence of

@@ -310,7 +310,6 @@ plus_event_kernel(const __grid_constant__ PlusKernelArgs a) {
     int64_t cube = -1, hi = 0;
     double s1 = 0.0, s2 = 0.0, fn = 1.0, rfn = 1.0;
     double coords[NDIM];
-    double hsum2 = 0.0;  // unused scalar partials (kept zero)
     for (int64_t e = begin + threadIdx.x; e < end; e += C::kThreads) {
         if (e >= hi) {
             if (cube >= 0) {
@@ -386,7 +385,8 @@ plus_event_kernel(const __grid_constant__ PlusKernelArgs a) {
         atomicAdd(&a.ress[cube], s1);
         atomicAdd(&a.ress2[cube], s2);
     }
-    write_partials<NDIM>(hsum2, hsum2, hist, do_hist, a.partials);
+    // per-cube sums went to ress/ress2; the block record carries no scalars here
+    write_partials<NDIM>(0.0, 0.0, hist, do_hist, a.partials);
 }
 
 // ---------------------------------------------------------------------------
