@@ -378,3 +378,30 @@ def test_rng_bits_32_option(alg):
     assert abs(res - 1.0) < 3 * err
     with pytest.raises(ValueError):
         alg(4, 1000, rng_bits=24)
+
+
+@pytest.mark.parametrize("alg", [PlainFlow, VegasFlow])
+def test_user_histograms(alg):
+    """examples/histogram_ex.py: the integrand accumulates weight*f into a 2-bin histogram of
+    x[:, 2]; run_integration empties it every iteration and leaves the weighted average
+    (monte_carlo.py:688-729).  The bins of a symmetric integrand each hold half the integral."""
+    from vegasflow_b200.utils import consume_array_into_indices
+
+    d, nbins = 3, 2
+    cumul = torch.zeros(nbins, dtype=torch.float64, device="cuda")
+
+    def integrand(xarr, weight=None):
+        res = example_integrand(xarr)
+        idx = torch.clamp((xarr[:, 2] * nbins).to(torch.int64), 0, nbins - 1)
+        cumul.add_(consume_array_into_indices(res * weight, idx.reshape(-1, 1), nbins))
+        return res
+
+    inst = alg(d, 100000, verbose=False)
+    inst.set_seed(321)
+    inst.compile(integrand, check=False)
+    res, err = inst.run_integration(4, histograms=(cumul,))
+    assert abs(res - 1.0) < 4 * err
+    h = cumul.cpu().numpy()
+    assert abs(h.sum() - res) < 1e-9 * abs(res)  # histogram entries add up to the integral
+    assert abs(h[0] - h[1]) < 8 * err
+    assert all(len(entry[2]) == 1 for entry in inst.history)  # per-iteration copies kept

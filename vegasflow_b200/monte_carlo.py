@@ -144,6 +144,7 @@ class MonteCarloFlow(ABC):
         self._results = None
         self._exchange = None
         self._exchange_tried = False
+        self._last_row = None
 
     # ------------------------------------------------------------------ state
     def _ensure_device(self):
@@ -168,6 +169,7 @@ class MonteCarloFlow(ABC):
             self._results = grown
         rows = self._results[self._results_used : self._results_used + n]
         self._results_used += n
+        self._last_row = rows[n - 1]
         return rows
 
     def _result_slot(self):
@@ -500,17 +502,17 @@ class MonteCarloFlow(ABC):
         `verbose=False` the host synchronises once, after the last iteration.
         With `verbose=True` every iteration is logged as it finishes, like the
         reference (one small device->host read per iteration).
-        `histograms` (user observables filled inside python integrands) is out
-        of scope and must be None.
+        `histograms`: tuple of torch tensors that a python integrand accumulates into
+        (monte_carlo.py:688-729): they are copied and emptied after every iteration and end up
+        holding the inverse-variance weighted average over iterations.
         """
-        if histograms is not None:
-            raise NotImplementedError("user histograms are out of scope of the B200 engine")
         if not self.event:
             raise RuntimeError("Compile must be ran before running any iterations")
         self._ensure_device()
         all_results = []
         first_slot = len(self._history)
-        rows = None if self._verbose else self._run_batched(n_iter)
+        histo_results = []
+        rows = None if (self._verbose or histograms) else self._run_batched(n_iter)
         batched = rows is not None
         if batched:
             for k in range(n_iter):
@@ -518,10 +520,23 @@ class MonteCarloFlow(ABC):
                 self._history.append((rows[k, 0], rows[k, 1], None))
         for i in range(0 if batched else n_iter):
             start = time.time() if log_time else None
+            self._last_row = None
             res, error = self._run_iteration()
             all_results.append((res, error))
+            # monte_carlo.py:688-694: store the user histograms of this iteration and empty them
+            hist_copy = None
+            if histograms:
+                hist_copy = tuple(h.clone() for h in histograms)
+                histo_results.append(hist_copy)
+                for h in histograms:
+                    h.zero_()
             if self._verbose:
-                res_h, err_h = self._to_host(res), self._to_host(error)
+                if self._last_row is not None:  # one 16-byte device->host read
+                    res_h, err_h = self._last_row.tolist()
+                    res, error = res_h, err_h
+                    all_results[-1] = (res, error)
+                else:
+                    res_h, err_h = self._to_host(res), self._to_host(error)
                 time_str = f"(took {time.time()-start:.5f} s)" if log_time else ""
                 if self._vectorial:
                     all_info = [
@@ -531,7 +546,7 @@ class MonteCarloFlow(ABC):
                 else:
                     all_info = [print_iteration(i, res_h, err_h, extra=time_str)]
                 logger.info("\n      ".join(all_info))
-            self._history.append((res, error, None))
+            self._history.append((res, error, hist_copy))
 
         # One read-back for everything that is still on the device
         if batched:
@@ -539,15 +554,21 @@ class MonteCarloFlow(ABC):
         else:
             host = [(self._to_host(r), self._to_host(e)) for r, e in all_results]
         for k, (r, e) in enumerate(host):
-            self._history[first_slot + k] = (r, e, None)
+            self._history[first_slot + k] = (r, e, self._history[first_slot + k][2])
 
         # monte_carlo.py:713-732
         aux_res = 0.0
         weight_sum = 0.0
-        for res, sigma in host:
+        for i, (res, sigma) in enumerate(host):
             wgt_tmp = 1.0 / np.power(sigma, 2)
             aux_res = aux_res + res * wgt_tmp
             weight_sum = weight_sum + wgt_tmp
+            if histograms:  # monte_carlo.py:721-725
+                for aux_h, curr_h in zip(histograms, histo_results[i]):
+                    aux_h.add_(curr_h * float(np.mean(wgt_tmp)))
+        if histograms:  # monte_carlo.py:727-729
+            for histogram in histograms:
+                histogram.div_(float(np.mean(weight_sum)))
         final_result = aux_res / weight_sum
         sigma = np.sqrt(1.0 / weight_sum)
         if self._verbose:
@@ -562,6 +583,22 @@ class MonteCarloFlow(ABC):
         if self._vectorial:
             return np.asarray(final_result), np.asarray(sigma)
         return float(final_result), float(sigma)
+
+    def run_iteration(self):
+        """One iteration through the public path, results on the host: `(res, sigma)` as floats
+        (arrays for vectorial integrands).  One small device->host read, like the per-iteration
+        logging of the reference's run_integration (monte_carlo.py:685-710)."""
+        if not self.event:
+            raise RuntimeError("Compile must be ran before running any iterations")
+        self._ensure_device()
+        self._last_row = None
+        res, error = self._run_iteration()
+        if self._last_row is not None:
+            res, error = self._last_row.tolist()
+        else:
+            res, error = self._to_host(res), self._to_host(error)
+        self._history.append((res, error, None))
+        return res, error
 
     @staticmethod
     def _to_host(v):
