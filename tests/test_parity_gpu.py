@@ -110,7 +110,9 @@ def test_digest_against_golden(lib, golden, name, d):
 
 @pytest.mark.parametrize("name,d,n", [("symgauss", 4, 200000), ("symgauss", 8, 100000),
                                        ("symgauss", 20, 50000), ("product", 8, 100000),
-                                       ("product", 5, 50000), ("symgauss", 1, 50000)])
+                                       ("product", 5, 50000), ("symgauss", 1, 50000),
+                                       ("symgauss", 9, 30000), ("product", 13, 30000),
+                                       ("symgauss", 19, 30000), ("product", 17, 30000)])
 def test_digest_against_c_oracle_large(lib, name, d, n):
     rng = np.random.default_rng(d * 1000 + n)
     r = R.TECH_CUT + rng.random((n, d)) * (1 - 2 * R.TECH_CUT)
@@ -380,11 +382,11 @@ def test_abi_error_codes_on_device(lib):
                           _lib.ptr(packed[d * 50:]), _lib.ptr(packed), 0, _lib.ptr(ws), 128,
                           _lib.stream_ptr())
     assert rc == -4 and "workspace" in _lib.last_error()
-    ws = torch.zeros(lib.vf_workspace_bytes(9) // 8, dtype=torch.float64, device=dev())
-    rc = lib.vf_run_event(1, 0, 9, 0, 10, 1.0, 0, 0, 0, _lib.ptr(grid), None, None,
+    ws = torch.zeros(lib.vf_workspace_bytes(21) // 8, dtype=torch.float64, device=dev())
+    rc = lib.vf_run_event(1, 0, 21, 0, 10, 1.0, 0, 0, 0, _lib.ptr(grid), None, None,
                           _lib.ptr(packed), None, 0, _lib.ptr(ws), ws.numel() * 8,
                           _lib.stream_ptr())
-    assert rc == -2  # n_dim = 9 has no fused instantiation
+    assert rc == -2  # n_dim = 21 has no fused instantiation (1..20 do)
     rc = lib.vf_run_event(1, 2, 3, 0, 10, 1.0, 0, 0, 0, _lib.ptr(grid), None, None,
                           _lib.ptr(packed), None, 0, _lib.ptr(ws), ws.numel() * 8,
                           _lib.stream_ptr())

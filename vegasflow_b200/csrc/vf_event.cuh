@@ -418,7 +418,9 @@ template <class I> int launch_plus(const PlusLaunch& L);
 template <class I> int supported_dim(int n_dim);
 
 // dims with a fused instantiation for the dimension-generic integrands
-#define VF_FOREACH_DIM(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(10) X(12) X(16) X(20)
+#define VF_FOREACH_DIM(X)                                                                  \
+    X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16) \
+    X(17) X(18) X(19) X(20)
 
 inline int grid_blocks_for(int64_t n_events, int threads, int min_blocks_per_sm) {
     const int64_t max_blocks = (int64_t)sm_count() * min_blocks_per_sm;
