@@ -54,6 +54,7 @@ extern "C" {
 #define VF_INTEGRAND_PRODUCT 1      /* README.md:63-68 */
 #define VF_INTEGRAND_DRELLYAN_LO 2  /* examples/drellyan_lo_tf.py:27-249, n_dim 4 */
 #define VF_INTEGRAND_SINGLETOP_LO 3 /* examples/singletop_lo_tf.py:45-270, n_dim 3 */
+#define VF_INTEGRAND_USER_BASE 16   /* ids returned by vf_register_user_integrand */
 
 /* error codes */
 #define VF_OK 0
@@ -67,6 +68,17 @@ const char* vf_last_error(void);
 
 /* Name -> id: "symgauss", "product", "drellyan_lo", "singletop_lo"; <0 if unknown. */
 int vf_integrand_id(const char* name);
+/*
+ * Register a user integrand compiled into its own module: a shared library built from
+ * vegasflow_b200/csrc/vf_user_integrand.cu.in around the user's
+ *     __device__ double integrand(const double* x, int n_dim)
+ * (see vegasflow_b200.integrands.cuda_integrand, which drives nvcc).  The fused kernels are
+ * instantiated for that function inside the module, so it runs inline in the event kernel
+ * exactly like the built-ins.  Native counterpart of the reference's "integrand in C / CUDA"
+ * examples (examples/simgauss_cffi.py:25-62, examples/cuda/integrand.cpp:41-89), which also
+ * compile user code at run time.  Returns the new integrand id (>= VF_INTEGRAND_USER_BASE).
+ */
+int vf_register_user_integrand(const char* module_path);
 /* 1 if the fused kernel is instantiated for (integrand, n_dim), else 0. */
 int vf_supported(int integrand, int n_dim);
 /* Algorithmic fp64 flops per event of the fused iteration. */

@@ -258,3 +258,33 @@ def test_two_rank_sharding_matches_single_rank_gloo(tmp_path):
     single = np.concatenate([hist.reshape(-1), [s1, s2]])
     np.testing.assert_allclose(r0[: d * 50 + 2], single, rtol=1e-11)
     np.testing.assert_allclose(r0[d * 50 + 2 :], co.refine_grid(hist, grid).reshape(-1), atol=1e-12)
+
+
+USER_SYMGAUSS = r"""
+__device__ double integrand(const double* x, int n_dim) {
+    // examples/simgauss_cffi.py:25-47 restated as a CUDA device function
+    const double a = 0.1;
+    double pref = 1.0;
+    for (int i = 0; i < n_dim; ++i) pref *= 1.0 / a / sqrt(M_PI);
+    double coef = 0.0;
+    for (int i = 0; i < n_dim; ++i) { const double t = (x[i] - 0.5) / a; coef += t * t; }
+    return pref * exp(-coef);
+}
+"""
+
+
+def test_user_cuda_integrand_compiles_and_registers():
+    """nvcc cross-compiles the module without a GPU; the library loads and registers it."""
+    h = vf.integrands.cuda_integrand(USER_SYMGAUSS, 3, name="test_user_symgauss")
+    assert os.path.exists(h.module_path)
+    iid = h.integrand_id()
+    assert iid >= 16 and h.integrand_id() == iid  # registered once
+    assert h.supported(3) and not h.supported(4)
+    lib = _lib.load()
+    assert lib.vf_register_user_integrand(b"/nonexistent/module.so") == -1
+    assert "cannot load" in _lib.last_error()
+    with pytest.raises(ValueError, match="nvcc failed"):
+        vf.integrands.cuda_integrand("this is not CUDA", 2, name="test_bad")
+    inst = vf.VegasFlow(4, 1000, verbose=False)
+    with pytest.raises(ValueError):
+        inst.compile(h)  # 3-dimensional integrand, 4-dimensional integrator

@@ -20,6 +20,7 @@ _SIGNATURES = {
     "vf_version": (C.c_int, []),
     "vf_last_error": (C.c_char_p, []),
     "vf_integrand_id": (C.c_int, [C.c_char_p]),
+    "vf_register_user_integrand": (C.c_int, [C.c_char_p]),
     "vf_supported": (C.c_int, [C.c_int, C.c_int]),
     "vf_flops_per_event": (C.c_double, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "vf_workspace_bytes": (C.c_size_t, [C.c_int]),

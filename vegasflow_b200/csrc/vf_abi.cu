@@ -3,7 +3,10 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <vector>
+
+#include <dlfcn.h>
 
 #include "vf_aux.cuh"
 #include "vf_event.cuh"
@@ -127,17 +130,61 @@ static int check_common(int n_dim, int64_t n) {
     return VF_OK;
 }
 
-template <class F>
-static int dispatch_integrand(int integrand, F&& f) {
+// ---- user integrands: separately compiled modules (vf_register_user_integrand) -------------
+struct UserIntegrandEntry {
+    void* handle;
+    int (*event)(const EventLaunch*);
+    int (*digest)(const DigestLaunch*);
+    int (*plus)(const PlusLaunch*);
+    int (*supported)(int);
+};
+static std::vector<UserIntegrandEntry> g_user;
+static std::mutex g_user_mutex;
+
+static const UserIntegrandEntry* user_entry(int integrand) {
+    std::lock_guard<std::mutex> lock(g_user_mutex);
+    const int k = integrand - VF_INTEGRAND_USER_BASE;
+    if (k < 0 || k >= (int)g_user.size()) return nullptr;
+    return &g_user[k];
+}
+
+static int unknown_integrand(int integrand) {
+    set_error("unknown integrand id %d", integrand);
+    return VF_ERR_INVALID;
+}
+
+static int do_launch_event(int integrand, const EventLaunch& L) {
     switch (integrand) {
-        case VF_INTEGRAND_SYMGAUSS: return f(SymGauss{});
-        case VF_INTEGRAND_PRODUCT: return f(Product{});
-        case VF_INTEGRAND_DRELLYAN_LO: return f(DrellYanLO{});
-        case VF_INTEGRAND_SINGLETOP_LO: return f(SingleTopLO{});
-        default:
-            set_error("unknown integrand id %d", integrand);
-            return VF_ERR_INVALID;
+        case VF_INTEGRAND_SYMGAUSS: return launch_event<SymGauss>(L);
+        case VF_INTEGRAND_PRODUCT: return launch_event<Product>(L);
+        case VF_INTEGRAND_DRELLYAN_LO: return launch_event<DrellYanLO>(L);
+        case VF_INTEGRAND_SINGLETOP_LO: return launch_event<SingleTopLO>(L);
+        default: break;
     }
+    if (const UserIntegrandEntry* u = user_entry(integrand)) return u->event(&L);
+    return unknown_integrand(integrand);
+}
+static int do_launch_digest(int integrand, const DigestLaunch& L) {
+    switch (integrand) {
+        case VF_INTEGRAND_SYMGAUSS: return launch_digest<SymGauss>(L);
+        case VF_INTEGRAND_PRODUCT: return launch_digest<Product>(L);
+        case VF_INTEGRAND_DRELLYAN_LO: return launch_digest<DrellYanLO>(L);
+        case VF_INTEGRAND_SINGLETOP_LO: return launch_digest<SingleTopLO>(L);
+        default: break;
+    }
+    if (const UserIntegrandEntry* u = user_entry(integrand)) return u->digest(&L);
+    return unknown_integrand(integrand);
+}
+static int do_launch_plus(int integrand, const PlusLaunch& L) {
+    switch (integrand) {
+        case VF_INTEGRAND_SYMGAUSS: return launch_plus<SymGauss>(L);
+        case VF_INTEGRAND_PRODUCT: return launch_plus<Product>(L);
+        case VF_INTEGRAND_DRELLYAN_LO: return launch_plus<DrellYanLO>(L);
+        case VF_INTEGRAND_SINGLETOP_LO: return launch_plus<SingleTopLO>(L);
+        default: break;
+    }
+    if (const UserIntegrandEntry* u = user_entry(integrand)) return u->plus(&L);
+    return unknown_integrand(integrand);
 }
 
 }  // namespace vf
@@ -165,8 +212,42 @@ int vf_supported(int integrand, int n_dim) {
         case VF_INTEGRAND_PRODUCT: return supported_dim<Product>(n_dim);
         case VF_INTEGRAND_DRELLYAN_LO: return supported_dim<DrellYanLO>(n_dim);
         case VF_INTEGRAND_SINGLETOP_LO: return supported_dim<SingleTopLO>(n_dim);
-        default: return 0;
+        default: break;
     }
+    if (const UserIntegrandEntry* u = user_entry(integrand)) return u->supported(n_dim);
+    return 0;
+}
+
+int vf_register_user_integrand(const char* module_path) {
+    if (!module_path) {
+        set_error("vf_register_user_integrand: null path");
+        return VF_ERR_INVALID;
+    }
+    void* h = dlopen(module_path, RTLD_NOW | RTLD_LOCAL);
+    if (!h) {
+        set_error("cannot load integrand module %s: %s", module_path, dlerror());
+        return VF_ERR_INVALID;
+    }
+    UserIntegrandEntry e;
+    e.handle = h;
+    e.event = (int (*)(const EventLaunch*))dlsym(h, "vfu_launch_event");
+    e.digest = (int (*)(const DigestLaunch*))dlsym(h, "vfu_launch_digest");
+    e.plus = (int (*)(const PlusLaunch*))dlsym(h, "vfu_launch_plus");
+    e.supported = (int (*)(int))dlsym(h, "vfu_supported_dim");
+    int (*abi)(void) = (int (*)(void))dlsym(h, "vfu_abi_version");
+    if (!e.event || !e.digest || !e.plus || !e.supported || !abi) {
+        set_error("%s does not export the vfu_* entry points", module_path);
+        dlclose(h);
+        return VF_ERR_INVALID;
+    }
+    if (abi() != VF_ABI_VERSION) {
+        set_error("%s was built against ABI %d, library is %d", module_path, abi(), VF_ABI_VERSION);
+        dlclose(h);
+        return VF_ERR_INVALID;
+    }
+    std::lock_guard<std::mutex> lock(g_user_mutex);
+    g_user.push_back(e);
+    return VF_INTEGRAND_USER_BASE + (int)g_user.size() - 1;
 }
 
 double vf_flops_per_event(int mode, int integrand, int n_dim, int plus) {
@@ -231,7 +312,7 @@ int vf_run_event(int mode, int integrand, int n_dim, uint64_t ev_begin, int64_t 
     L.k.pk = make_philox_keys(seed);
     L.k.iteration = iteration;
     L.k.train = train;
-    rc = dispatch_integrand(integrand, [&](auto tag) { return launch_event<decltype(tag)>(L); });
+    rc = do_launch_event(integrand, L);
     if (rc) return rc;
     return launch_finalize((double*)workspace, nblocks, n_dim, with_hist, out_sums, out_hist,
                            accumulate, L.stream);
@@ -279,8 +360,7 @@ int vf_run_iterations(int mode, int integrand, int n_dim, int64_t n_events, uint
     double* out_sums = packed + (size_t)n_dim * kBins;
     for (int it = 0; it < n_iter; ++it) {
         L.k.iteration = first_iteration + (uint32_t)it;
-        rc = dispatch_integrand(integrand,
-                                [&](auto tag) { return launch_event<decltype(tag)>(L); });
+        rc = do_launch_event(integrand, L);
         if (rc) return rc;
         rc = launch_finalize_epilogue((double*)workspace, nblocks, n_dim, with_hist, n_events,
                                       train, out_sums, out_hist, divisions, results + 2 * it,
@@ -343,8 +423,7 @@ int vf_run_iterations_sharded(int mode, int integrand, int n_dim, uint64_t ev_be
         peers.base[p] = p < world ? (unsigned long long*)(uintptr_t)peer_buffers[p] : nullptr;
     for (int it = 0; it < n_iter; ++it) {
         L.k.iteration = first_iteration + (uint32_t)it;
-        rc = dispatch_integrand(integrand,
-                                [&](auto tag) { return launch_event<decltype(tag)>(L); });
+        rc = do_launch_event(integrand, L);
         if (rc) return rc;
         rc = launch_exchange_epilogue((double*)workspace, nblocks, n_dim, with_hist,
                                       n_events_total, train, packed + (size_t)n_dim * kBins, packed,
@@ -399,8 +478,7 @@ int vf_digest_from_uniforms(int mode, int integrand, int n_dim, int64_t n, const
     L.k.wf = wf;
     L.k.n = n;
     L.k.xjac = xjac;
-    return dispatch_integrand(integrand,
-                              [&](auto tag) { return launch_digest<decltype(tag)>(L); });
+    return do_launch_digest(integrand, L);
 }
 
 int vf_uniforms(int n_dim, uint64_t ev_begin, int64_t n, uint64_t seed, uint32_t iteration,
@@ -507,7 +585,7 @@ int vfp_run_event(int integrand, int n_dim, int n_strat, int64_t n_cubes, int64_
     L.k.pk = make_philox_keys(seed);
     L.k.iteration = iteration;
     L.k.train = train;
-    rc = dispatch_integrand(integrand, [&](auto tag) { return launch_plus<decltype(tag)>(L); });
+    rc = do_launch_plus(integrand, L);
     if (rc) return rc;
     if (!train) return VF_OK;
     // histogram only: the scalar block writes into a scratch pair past the partial records

@@ -11,7 +11,10 @@ Reference bodies (file:line relative to /root/reference):
   drellyan_lo   examples/drellyan_lo_tf.py:27-249   (n_dim = 4)
   singletop_lo  examples/singletop_lo_tf.py:45-270  (n_dim = 3)
 """
+import hashlib
 import math
+import os
+import subprocess
 
 import torch
 
@@ -45,6 +48,73 @@ class BuiltinIntegrand:
 
     def __repr__(self):
         return f"<builtin integrand {self.name}>"
+
+
+class CudaIntegrand(BuiltinIntegrand):
+    """A user integrand written as a CUDA device function and compiled into the fused kernels.
+
+    The native counterpart of the reference's "integrand in C / CUDA" examples
+    (examples/simgauss_cffi.py:25-62, examples/cuda/integrand.cpp:41-89): instead of a C function
+    called through cffi on host arrays, or a TensorFlow custom op, the source is instantiated
+    INSIDE the event kernel, so it runs inline like the built-in integrands (no per-event data in
+    HBM).  Use `cuda_integrand(source, n_dim)` to build one.
+    """
+
+    def __init__(self, name, n_dim, module_path):
+        super().__init__(name, fixed_dim=n_dim)
+        self.module_path = module_path
+        self._id = None
+
+    def integrand_id(self):
+        if self._id is None:
+            from vegasflow_b200 import _lib
+
+            iid = _lib.load().vf_register_user_integrand(self.module_path.encode())
+            _lib.check(min(iid, 0))
+            self._id = iid
+        return self._id
+
+
+def cuda_integrand(source, n_dim, name="user_integrand", heavy=False, verbose=False):
+    """Compile `source` (CUDA C++ defining
+    ``__device__ double integrand(const double* x, int n_dim)``) into a module that
+    instantiates the fused kernels for it, and return a handle for `compile()`.
+
+    `heavy=True` gives the kernel the 128-register budget (one block per SM), for integrands
+    the size of a matrix element.  nvcc cross-compiles, so this works without a GPU; modules
+    are cached under vegasflow_b200/build/user/ by source hash.
+    """
+    from vegasflow_b200 import build as vf_build
+
+    n_dim = int(n_dim)
+    if not 1 <= n_dim <= 32:
+        raise ValueError("cuda_integrand supports 1 <= n_dim <= 32")
+    lib_so = vf_build.build()
+    with open(os.path.join(vf_build.CSRC, "vf_user_integrand.cu.in")) as fh:
+        template = fh.read()
+    unit = (template.replace("@USER_SOURCE@", source).replace("@N_DIM@", str(n_dim))
+            .replace("@HEAVY@", "true" if heavy else "false"))
+    # the module is tied to this build of the library (struct layouts, ABI version)
+    stamp = f"{os.path.getmtime(lib_so):.0f}"
+    digest = hashlib.sha256((unit + stamp).encode()).hexdigest()[:20]
+    out_dir = os.path.join(vf_build.OBJDIR, "user")
+    os.makedirs(out_dir, exist_ok=True)
+    cu_path = os.path.join(out_dir, f"{name}_{digest}.cu")
+    so_path = os.path.join(out_dir, f"{name}_{digest}.so")
+    if not os.path.exists(so_path):
+        with open(cu_path, "w") as fh:
+            fh.write(unit)
+        flags = [f for f in vf_build.NVCC_FLAGS if f not in ("-Xptxas", "-v")]
+        cmd = [vf_build._nvcc(), *flags, "-shared", "-I", vf_build.INCLUDE, "-I", vf_build.CSRC,
+               cu_path, "-o", so_path + ".tmp", "-L", vf_build.LIBDIR, "-lvegasflow_b200",
+               "-Xlinker", "-rpath", "-Xlinker", vf_build.LIBDIR]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise ValueError(f"nvcc failed on the user integrand:\n{res.stdout}\n{res.stderr}")
+        if verbose:
+            print(res.stderr)
+        os.replace(so_path + ".tmp", so_path)
+    return CudaIntegrand(name, n_dim, so_path)
 
 
 def _symgauss_torch(xarr):
