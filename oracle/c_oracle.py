@@ -15,10 +15,22 @@ MODE_PLAIN, MODE_VEGAS = 0, 1
 INTEGRAND_IDS = {"symgauss": 0, "product": 1}
 
 
-def build(force=False):
+def _stale():
     src = os.path.join(_HERE, "vegas_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
-        subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "libvegas_oracle.so"])
+    return not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src)
+
+
+def build(force=False):
+    if force or _stale():
+        import fcntl
+
+        with open(os.path.join(_HERE, ".build.lock"), "w") as lock:  # one builder at a time
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            try:
+                if force or _stale():
+                    subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "libvegas_oracle.so"])
+            finally:
+                fcntl.flock(lock, fcntl.LOCK_UN)
     return _SO
 
 

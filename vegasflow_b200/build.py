@@ -7,6 +7,8 @@ nvcc cross-compiles without a GPU.  -fmad=false keeps every multiply/add on the
 reference arithmetic path separately rounded (explicit fma() calls are kept).
 """
 import argparse
+import fcntl
+import hashlib
 import os
 import subprocess
 import sys
@@ -41,11 +43,24 @@ def _deps():
     return out
 
 
+HASH_PATH = os.path.join(LIBDIR, "libvegasflow_b200.sha256")
+
+
+def source_hash():
+    """Content hash of everything the library is built from (mtimes do not survive copies)."""
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for path in sorted(_deps()):
+        h.update(os.path.basename(path).encode())
+        with open(path, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
 def needs_build():
-    if not os.path.exists(SO_PATH):
+    if not os.path.exists(SO_PATH) or not os.path.exists(HASH_PATH):
         return True
-    t = os.path.getmtime(SO_PATH)
-    return any(os.path.getmtime(d) > t for d in _deps())
+    with open(HASH_PATH) as fh:
+        return fh.read().strip() != source_hash()
 
 
 def build(force=False, verbose=False):
@@ -53,7 +68,20 @@ def build(force=False, verbose=False):
         return SO_PATH
     os.makedirs(LIBDIR, exist_ok=True)
     os.makedirs(OBJDIR, exist_ok=True)
+    # one builder at a time (torchrun starts one process per GPU on the same tree)
+    with open(os.path.join(LIBDIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():  # another process built it while we waited
+                return SO_PATH
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose):
     nvcc = _nvcc()
+    digest = source_hash()
 
     def compile_one(src):
         obj = os.path.join(OBJDIR, src.replace(".cu", ".o"))
@@ -69,10 +97,14 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [nvcc, "-shared", "-o", SO_PATH, *objs, "-lcudart", "-ldl"]
+    tmp = SO_PATH + ".tmp"
+    cmd = [nvcc, "-shared", "-o", tmp, *objs, "-lcudart", "-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, SO_PATH)  # atomic: a concurrent loader never sees a half-written library
+    with open(HASH_PATH, "w") as fh:
+        fh.write(digest + "\n")
     return SO_PATH
 
 

@@ -89,13 +89,13 @@ def cuda_integrand(source, n_dim, name="user_integrand", heavy=False, verbose=Fa
     n_dim = int(n_dim)
     if not 1 <= n_dim <= 32:
         raise ValueError("cuda_integrand supports 1 <= n_dim <= 32")
-    lib_so = vf_build.build()
+    vf_build.build()
     with open(os.path.join(vf_build.CSRC, "vf_user_integrand.cu.in")) as fh:
         template = fh.read()
     unit = (template.replace("@USER_SOURCE@", source).replace("@N_DIM@", str(n_dim))
             .replace("@HEAVY@", "true" if heavy else "false"))
     # the module is tied to this build of the library (struct layouts, ABI version)
-    stamp = f"{os.path.getmtime(lib_so):.0f}"
+    stamp = vf_build.source_hash()
     digest = hashlib.sha256((unit + stamp).encode()).hexdigest()[:20]
     out_dir = os.path.join(vf_build.OBJDIR, "user")
     os.makedirs(out_dir, exist_ok=True)
