@@ -118,6 +118,8 @@ def cpu_reference_run(wl, steps, warmup, sample_events):
 
     if wl["integrand"] not in T.INTEGRANDS or wl["alg"] != "vegas":
         return None
+    # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1)
+    torch.set_num_threads(os.cpu_count() or 1)
     evs, dt, _ = T.time_iterations(wl["integrand"], wl["n_dim"], sample_events, steps,
                                    warmup=warmup)
     return dict(value=evs, unit=UNIT, cores=torch.get_num_threads(), kind="port",
@@ -135,10 +137,12 @@ def cpu_best_effort(wl, sample_events):
     if wl["integrand"] not in co.INTEGRAND_IDS or wl["alg"] != "vegas":
         return None
     grid = R.initial_divisions(wl["n_dim"])
-    co.run_event(1, wl["integrand"], wl["n_dim"], 0, sample_events // 10, 1.0, 1, 0, True, grid)
+    nthreads = os.cpu_count() or 1
+    co.run_event(1, wl["integrand"], wl["n_dim"], 0, sample_events // 10, 1.0, 1, 0, True, grid,
+                 nthreads=nthreads)
     t0 = time.perf_counter()
     co.run_event(1, wl["integrand"], wl["n_dim"], 0, sample_events, 1.0 / sample_events, 1, 1, True,
-                 grid)
+                 grid, nthreads=nthreads)
     dt = time.perf_counter() - t0
     return dict(value=sample_events / dt, unit=UNIT, cores=os.cpu_count(), kind="port",
                 sample=f"1 fused iteration x {sample_events} events, C/OpenMP restatement, {dt:.2f} s")
