@@ -495,3 +495,42 @@ def test_rng32_stream_fused_kernel_against_oracle(lib):
         np.testing.assert_array_equal(w.cpu().numpy(), wo)
     finally:
         co.set_rng_bits(52)
+
+
+@pytest.mark.parametrize("name,d,n", [("symgauss", 8, 10**8), ("product", 8, 10**7),
+                                       ("symgauss", 20, 125 * 10**6), ("symgauss", 4, 10**6)])
+def test_full_size_properties(lib, name, d, n):
+    """BASELINE.json sizes (per GPU), checked through size-independent properties: every event
+    lands in exactly one bin of every dimension (checksum of the histogram rows == sum (wf)^2),
+    the range splits add up, the flat-grid estimate is within 5 sigma of the analytic integral,
+    and one refinement keeps the grid a strictly increasing partition of [0, 1]."""
+    iid = lib.vf_integrand_id(name.encode())
+    grid = R.initial_divisions(d)
+    s1, s2, hist = gpu_run_event(lib, 1, iid, d, 0, n, 1.0 / n, 2026, 0, True, grid)
+    np.testing.assert_allclose(hist.sum(axis=1), np.full(d, s2), rtol=1e-10)
+    assert (hist >= 0).all()
+    sigma = R.vegas_sigma(s1, s2, n)
+    exact = 1.0 if name == "symgauss" else 2.0**-d
+    assert abs(s1 - exact) < 5 * sigma
+    cut = n // 3
+    a = gpu_run_event(lib, 1, iid, d, 0, cut, 1.0 / n, 2026, 0, True, grid)
+    b = gpu_run_event(lib, 1, iid, d, cut, n - cut, 1.0 / n, 2026, 0, True, grid)
+    assert abs((a[0] + b[0]) - s1) <= 1e-11 * abs(s1)
+    np.testing.assert_allclose(a[2] + b[2], hist, rtol=1e-9, atol=1e-300)
+    t_h, t_g = to_dev(hist), to_dev(grid)
+    _lib.check(lib.vf_refine_grid(d, _lib.ptr(t_h), _lib.ptr(t_g), _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    new = t_g.cpu().numpy()
+    assert (np.diff(new, axis=1) > 0).all() and (new[:, 0] == 0).all() and (new[:, -1] == 1).all()
+    # symmetric integrands keep a grid that is symmetric about 1/2 (to the histogram noise)
+    if name == "symgauss":
+        assert np.abs(new + new[:, ::-1] - 1.0).max() < 0.05
+
+
+def test_refine_flat_histogram_is_identity(lib):
+    d = 5
+    t_h = to_dev(np.full((d, 50), 3.7e-9))
+    t_g = to_dev(R.initial_divisions(d))
+    _lib.check(lib.vf_refine_grid(d, _lib.ptr(t_h), _lib.ptr(t_g), _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(t_g.cpu().numpy(), R.initial_divisions(d), rtol=0, atol=1e-12)
