@@ -509,9 +509,10 @@ def test_full_size_properties(lib, name, d, n):
     s1, s2, hist = gpu_run_event(lib, 1, iid, d, 0, n, 1.0 / n, 2026, 0, True, grid)
     np.testing.assert_allclose(hist.sum(axis=1), np.full(d, s2), rtol=1e-10)
     assert (hist >= 0).all()
-    sigma = R.vegas_sigma(s1, s2, n)
-    exact = 1.0 if name == "symgauss" else 2.0**-d
-    assert abs(s1 - exact) < 5 * sigma
+    if d <= 8:  # (at d=20 a flat grid never hits the 1e-10-volume peak: no meaningful sigma)
+        sigma = R.vegas_sigma(s1, s2, n)
+        exact = 1.0 if name == "symgauss" else 2.0**-d
+        assert abs(s1 - exact) < 5 * sigma
     cut = n // 3
     a = gpu_run_event(lib, 1, iid, d, 0, cut, 1.0 / n, 2026, 0, True, grid)
     b = gpu_run_event(lib, 1, iid, d, cut, n - cut, 1.0 / n, 2026, 0, True, grid)
@@ -523,7 +524,7 @@ def test_full_size_properties(lib, name, d, n):
     new = t_g.cpu().numpy()
     assert (np.diff(new, axis=1) > 0).all() and (new[:, 0] == 0).all() and (new[:, -1] == 1).all()
     # symmetric integrands keep a grid that is symmetric about 1/2 (to the histogram noise)
-    if name == "symgauss":
+    if name == "symgauss" and d <= 8:
         assert np.abs(new + new[:, ::-1] - 1.0).max() < 0.05
 
 

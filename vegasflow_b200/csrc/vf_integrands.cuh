@@ -145,10 +145,13 @@ __device__ __forceinline__ Angles angles_acos(const Mom& p) {
         if (ry < 0.0) phi = -phi;
     }
     Angles a;
-    a.ch = cos(theta / 2);
-    a.sh = sin(theta / 2);
-    a.cp = cos(phi);
-    a.sp = sin(phi);
+    sincos(theta / 2, &a.sh, &a.ch);  // one argument reduction for both
+    if (phi == 0.0) {                 // beam-axis momenta (and phi2 == 0): cos 0 = 1, sin 0 = 0
+        a.cp = 1.0;
+        a.sp = 0.0;
+    } else {
+        sincos(phi, &a.sp, &a.cp);
+    }
     a.pref = spinor_prefact(p.e);
     return a;
 }
@@ -168,10 +171,13 @@ __device__ __forceinline__ Angles angles_st_u0(const Mom& p) {
         phi = (rx < 0.0) ? M_PI : 0.0;
     }
     Angles a;
-    a.ch = cos(theta / 2);
-    a.sh = sin(theta / 2);
-    a.cp = cos(phi);
-    a.sp = sin(phi);
+    sincos(theta / 2, &a.sh, &a.ch);  // one argument reduction for both
+    if (phi == 0.0) {                 // beam-axis momenta (and phi2 == 0): cos 0 = 1, sin 0 = 0
+        a.cp = 1.0;
+        a.sp = 0.0;
+    } else {
+        sincos(phi, &a.sp, &a.cp);
+    }
     a.pref = spinor_prefact(p.e);
     return a;
 }
@@ -230,8 +236,7 @@ struct DrellYanLO {
         const double pVt2 = pV.x * pV.x + pV.y * pV.y;
         const double phi = (2.0 * M_PI) * xa[3];  // :60, 2*np.pi*x3
         double sphi, cphi;
-        sphi = sin(phi);
-        cphi = cos(phi);
+        sincos(phi, &sphi, &cphi);
         const double root = sqrt(mV2 + pVt2);
         const double ptmax = 0.5 * mV2 / (root - (pV.x * cphi + pV.y * sphi));
         const double pta = ptmax * xa[2];
