@@ -18,8 +18,11 @@ template <int NDIM>
 struct Cfg {
     static constexpr int kThreads = 512;
     static constexpr int kMinBlocks = (NDIM <= 8) ? 2 : 1;
-    static constexpr int TC = (NDIM <= 8) ? 8 : 4;
-    static constexpr int HC = (NDIM <= 8) ? 16 : ((NDIM <= 12) ? 8 : 4);
+    // d <= 8: two 512-thread blocks per SM (2 x 102 KB at d = 8); above that the register budget
+    // allows one block, which then takes up to 192 KB (d = 20) so that the table stays
+    // conflict-free (TC = 8) and the histogram keeps >= 8 copies.
+    static constexpr int TC = 8;
+    static constexpr int HC = (NDIM <= 12) ? 16 : 8;
     static constexpr int kTblEntries = NDIM * kBins * TC;
     static constexpr int kHistEntries = NDIM * kBins * HC;
     static constexpr size_t kSmemBytes = (size_t)kTblEntries * 16 + (size_t)kHistEntries * 8;
