@@ -37,7 +37,7 @@ constexpr int min_blocks() {
 // the event state; for d > 4 it needs the 128-register budget to stay spill-free.
 template <class I, int NDIM>
 constexpr int plus_min_blocks() {
-    return (NDIM <= 4 && !I::kHeavy) ? 2 : 1;
+    return (NDIM <= 8 && !I::kHeavy) ? 2 : 1;
 }
 
 struct EventKernelArgs {
