@@ -1,3 +1,4 @@
+# Every multi-rank command runs under `timeout`: a hung collective must not hold N GPUs.
 # usage: bash scripts/gpu_multi.sh <ngpus> <workloads...>   (run under gpurun --gpus N)
 N=${1:-2}; shift; WLS=${@:-c2 c5}
 mkdir -p gpurun_out
@@ -9,7 +10,7 @@ for w in $WLS; do
   for n in $(seq 2 $N); do
     case " 2 4 8 " in *" $n "*) ;; *) continue;; esac
     for x in p2p nccl; do
-      VEGASFLOW_B200_EXCHANGE=$x python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29655 bench.py --gpus $n --workload $w --steps 20 --warmup 3 > gpurun_out/scale_${w}_n${n}_$x.json 2> gpurun_out/scale_${w}_n${n}_$x.err
+      VEGASFLOW_B200_EXCHANGE=$x timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29655 bench.py --gpus $n --workload $w --steps 20 --warmup 3 > gpurun_out/scale_${w}_n${n}_$x.json 2> gpurun_out/scale_${w}_n${n}_$x.err
       show gpurun_out/scale_${w}_n${n}_$x.json "$w/$x"
     done
   done

@@ -288,3 +288,26 @@ def test_user_cuda_integrand_compiles_and_registers():
     inst = vf.VegasFlow(4, 1000, verbose=False)
     with pytest.raises(ValueError):
         inst.compile(h)  # 3-dimensional integrand, 4-dimensional integrator
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` runs on the host cores and prints ONE JSON line with the
+    driver's keys (the GPU arm is exercised on the B200 box)."""
+    import subprocess
+    import sys
+
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference",
+                          "--steps", "1", "--warmup", "1"], capture_output=True, text=True,
+                         timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.strip().splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step",
+                "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config",
+                "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["unit"] == "events/s" and d["value"] > 1e4
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["vs_baseline"] is None
+    assert "workload" in d["config"]

@@ -221,3 +221,30 @@ def test_flop_counts_match_the_abi_table():
         abi = lib.vf_flops_per_event(1, lib.vf_integrand_id(name.encode()), d, 0) - (12 * d + 5)
         # symgauss: SURVEY counts d adds for the reduce_sum, the restatement starts from term 0
         assert abs(abi - flops) <= 1, (name, d, abi, flops)
+
+
+def test_reference_shaped_cpu_port_is_the_same_algorithm():
+    """The torch-CPU port timed by `bench.py --impl reference` (oracle/ref_shaped_torch.py) and
+    the numpy oracle are two restatements of the same reference lines: identical bins, x and
+    histogram on the same uniforms (weights/sums up to the reduction order of torch.prod/sum)."""
+    import torch
+
+    from oracle import ref_shaped_torch as T
+
+    rng = np.random.default_rng(12)
+    d, n = 5, 4000
+    r = R.TECH_CUT + rng.random((n, d)) * (1 - 2 * R.TECH_CUT)
+    grid = np.sort(rng.random((d, 51)), axis=1)
+    grid[:, 0], grid[:, -1] = 0.0, 1.0
+    x, w, ind = T.generate_random_array(torch.from_numpy(r), torch.from_numpy(grid))
+    xo, wo, io = R.vegas_digest(r, grid)
+    np.testing.assert_array_equal(ind.numpy(), io)
+    np.testing.assert_array_equal(x.numpy(), xo)
+    np.testing.assert_allclose(w.numpy(), wo, rtol=1e-15)
+    f = T.symgauss(x).numpy()
+    np.testing.assert_allclose(f, R.symgauss(xo), rtol=1e-9)  # sum order inside (C + s) - C
+    tmp2 = (wo / n * R.symgauss(xo)) ** 2
+    h = T.consume_array_into_indices(torch.from_numpy(tmp2), ind[:, 2:3], 50).numpy()
+    np.testing.assert_allclose(h, R.consume_array_into_indices(tmp2, io[:, 2:3], 50), rtol=1e-12)
+    new = R.refine_grid(np.stack([h] * d), grid)
+    assert (np.diff(new, axis=1) >= 0).all()

@@ -68,6 +68,13 @@ class VegasFlowPlus(VegasFlow):
         self._plus_state = None
         if self._adaptive:
             logger.warning("Variable number of events requires function signatures all across")
+        from vegasflow_b200 import parallel
+
+        if parallel.world()[1] > 1:
+            logger.warning(
+                "VegasFlowPlus is single-device (like the reference): every rank runs the whole "
+                "iteration; use VegasFlow to shard events over GPUs"
+            )
 
     @property
     def xjac(self):
