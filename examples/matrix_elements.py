@@ -3,6 +3,10 @@
 
     python examples/matrix_elements.py
 """
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # repo root
 import vegasflow_b200 as vf
 
 if __name__ == "__main__":

@@ -4,6 +4,9 @@ reduce + NVLink exchange + refine kernel per iteration.
     torchrun --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 examples/multi_gpu.py
 """
 import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # repo root
 
 import torch
 import torch.distributed as dist

@@ -2,6 +2,10 @@
 
     python examples/vegasplus_and_grid.py
 """
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # repo root
 import tempfile
 
 import vegasflow_b200 as vf
