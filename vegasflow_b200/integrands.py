@@ -27,13 +27,16 @@ class BuiltinIntegrand:
         self.name = name
         self.fixed_dim = fixed_dim
         self._torch_impl = torch_impl
+        self._id = None
 
     def integrand_id(self):
-        from vegasflow_b200 import _lib
+        if self._id is None:
+            from vegasflow_b200 import _lib
 
-        iid = _lib.load().vf_integrand_id(self.name.encode())
-        _lib.check(min(iid, 0))
-        return iid
+            iid = _lib.load().vf_integrand_id(self.name.encode())
+            _lib.check(min(iid, 0))
+            self._id = iid
+        return self._id
 
     def supported(self, n_dim):
         from vegasflow_b200 import _lib
@@ -63,7 +66,6 @@ class CudaIntegrand(BuiltinIntegrand):
     def __init__(self, name, n_dim, module_path):
         super().__init__(name, fixed_dim=n_dim)
         self.module_path = module_path
-        self._id = None
 
     def integrand_id(self):
         if self._id is None:
