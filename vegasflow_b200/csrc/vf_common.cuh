@@ -1,7 +1,9 @@
 // Shared device/host definitions for the vegasflow_b200 kernels (sm_100a).
 // Reference citations are file:line relative to /root/reference.
 #pragma once
+#ifndef VF_HOST_SHIM  // tests/host_shim builds this header with g++ to test the device source
 #include <cuda_runtime.h>
+#endif
 #include <stdint.h>
 
 #include "../../include/vegasflow_b200.h"
