@@ -141,11 +141,13 @@ struct UserIntegrandEntry {
 static std::vector<UserIntegrandEntry> g_user;
 static std::mutex g_user_mutex;
 
-static const UserIntegrandEntry* user_entry(int integrand) {
+// Returns a COPY (the table may grow under another thread's registration).
+static bool user_entry(int integrand, UserIntegrandEntry* out) {
     std::lock_guard<std::mutex> lock(g_user_mutex);
     const int k = integrand - VF_INTEGRAND_USER_BASE;
-    if (k < 0 || k >= (int)g_user.size()) return nullptr;
-    return &g_user[k];
+    if (k < 0 || k >= (int)g_user.size()) return false;
+    *out = g_user[k];
+    return true;
 }
 
 static int unknown_integrand(int integrand) {
@@ -161,7 +163,8 @@ static int do_launch_event(int integrand, const EventLaunch& L) {
         case VF_INTEGRAND_SINGLETOP_LO: return launch_event<SingleTopLO>(L);
         default: break;
     }
-    if (const UserIntegrandEntry* u = user_entry(integrand)) return u->event(&L);
+    UserIntegrandEntry u;
+    if (user_entry(integrand, &u)) return u.event(&L);
     return unknown_integrand(integrand);
 }
 static int do_launch_digest(int integrand, const DigestLaunch& L) {
@@ -172,7 +175,8 @@ static int do_launch_digest(int integrand, const DigestLaunch& L) {
         case VF_INTEGRAND_SINGLETOP_LO: return launch_digest<SingleTopLO>(L);
         default: break;
     }
-    if (const UserIntegrandEntry* u = user_entry(integrand)) return u->digest(&L);
+    UserIntegrandEntry u;
+    if (user_entry(integrand, &u)) return u.digest(&L);
     return unknown_integrand(integrand);
 }
 static int do_launch_plus(int integrand, const PlusLaunch& L) {
@@ -183,7 +187,8 @@ static int do_launch_plus(int integrand, const PlusLaunch& L) {
         case VF_INTEGRAND_SINGLETOP_LO: return launch_plus<SingleTopLO>(L);
         default: break;
     }
-    if (const UserIntegrandEntry* u = user_entry(integrand)) return u->plus(&L);
+    UserIntegrandEntry u;
+    if (user_entry(integrand, &u)) return u.plus(&L);
     return unknown_integrand(integrand);
 }
 
@@ -214,7 +219,8 @@ int vf_supported(int integrand, int n_dim) {
         case VF_INTEGRAND_SINGLETOP_LO: return supported_dim<SingleTopLO>(n_dim);
         default: break;
     }
-    if (const UserIntegrandEntry* u = user_entry(integrand)) return u->supported(n_dim);
+    UserIntegrandEntry u;
+    if (user_entry(integrand, &u)) return u.supported(n_dim);
     return 0;
 }
 

@@ -2,6 +2,8 @@
 // reductions + shared-memory histograms, one launch per chunk of events.
 // Reference citations are file:line relative to /root/reference.
 #pragma once
+#include <atomic>
+
 #include "vf_common.cuh"
 #include "vf_integrands.cuh"
 
@@ -425,6 +427,12 @@ template <class I> int supported_dim(int n_dim);
     X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8) X(9) X(10) X(11) X(12) X(13) X(14) X(15) X(16) \
     X(17) X(18) X(19) X(20)
 
+inline int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev > 63) dev = 0;
+    return dev;
+}
+
 inline int grid_blocks_for(int64_t n_events, int threads, int min_blocks_per_sm) {
     const int64_t max_blocks = (int64_t)sm_count() * min_blocks_per_sm;
     // at least ~4 events per thread before adding blocks
@@ -440,11 +448,13 @@ int launch_event_dim(const EventLaunch& L) {
     using C = Cfg<NDIM>;
     auto kern = event_kernel<I, NDIM, MODE, RB>;
     const size_t smem = MODE == VF_MODE_VEGAS ? C::kSmemBytes : 0;
-    static bool configured = false;
-    if (!configured) {
+    // opt in to > 48 KB dynamic shared memory once per device (the attribute is per device)
+    static std::atomic<uint64_t> configured{0};
+    const int dev = current_device();
+    if (!(configured.load(std::memory_order_acquire) >> dev & 1ull)) {
         VF_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)C::kSmemBytes));
-        configured = true;
+        configured.fetch_or(1ull << dev, std::memory_order_release);
     }
     const int64_t n = (int64_t)(L.k.ev_end - L.k.ev_begin);
     const int blocks = grid_blocks_for(n, C::kThreads, min_blocks<I, NDIM>());
@@ -461,11 +471,13 @@ template <class I, int NDIM, int MODE>
 int launch_digest_dim(const DigestLaunch& L) {
     using C = Cfg<NDIM>;
     auto kern = digest_kernel<I, NDIM, MODE>;
-    static bool configured = false;
-    if (!configured) {
+    // opt in to > 48 KB dynamic shared memory once per device (the attribute is per device)
+    static std::atomic<uint64_t> configured{0};
+    const int dev = current_device();
+    if (!(configured.load(std::memory_order_acquire) >> dev & 1ull)) {
         VF_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            (int)C::kSmemBytes));
-        configured = true;
+        configured.fetch_or(1ull << dev, std::memory_order_release);
     }
     const int blocks = grid_blocks_for(L.k.n, C::kThreads, min_blocks<I, NDIM>());
     kern<<<blocks, C::kThreads, C::kSmemBytes, L.stream>>>(L.k);
