@@ -248,3 +248,34 @@ def test_reference_shaped_cpu_port_is_the_same_algorithm():
     np.testing.assert_allclose(h, R.consume_array_into_indices(tmp2, io[:, 2:3], 50), rtol=1e-12)
     new = R.refine_grid(np.stack([h] * d), grid)
     assert (np.diff(new, axis=1) >= 0).all()
+
+
+def test_unpinned_conventions_are_quantified():
+    """What "parity unpinned" means in numbers: TensorFlow/Eigen may sum the d terms
+    of symgauss in another order or contract a*b+c; the oracle fixes left-to-right, unfused.
+    The (C + s) - C quantisation turns a 1-ulp change of s into ulp(C) for ~1e-3 of the events;
+    everything that does not pass through that quantisation is insensitive at the 1e-15 level."""
+    rng = np.random.default_rng(5)
+    d = 8
+    x = rng.random((200000, d))
+    a = np.float64(0.1)
+    sq = ((x - 0.5) / a) ** 2
+    s_seq = sq[:, 0].copy()
+    for j in range(1, d):
+        s_seq = s_seq + sq[:, j]
+    s_pair = ((sq[:, 0] + sq[:, 1]) + (sq[:, 2] + sq[:, 3])) + ((sq[:, 4] + sq[:, 5]) +
+                                                                (sq[:, 6] + sq[:, 7]))
+    _, C = R.symgauss_constants(d)
+    f_seq = np.exp(-((C + s_seq) - C))
+    f_pair = np.exp(-((C + s_pair) - C))
+    rel = np.abs(f_seq - f_pair) / f_seq
+    flipped = (rel > 1e-12).mean()
+    assert 1e-5 < flipped < 5e-3          # ~ulp(s)/ulp(C) of the events move ...
+    assert rel.max() < 2 * 5.9e-11        # ... by one ulp(C) = 5.8e-11 at d = 8
+    # without the quantisation the two orders agree to a few ulp of s
+    plain = np.abs(np.exp(-s_seq) - np.exp(-s_pair)) / np.exp(-s_seq)
+    assert plain.max() < 1e-13
+    # the product integrand and the VEGAS weight are order-sensitive only at the ulp level
+    p_seq = R.product(x)
+    p_pair = ((x[:, 0] * x[:, 1]) * (x[:, 2] * x[:, 3])) * ((x[:, 4] * x[:, 5]) * (x[:, 6] * x[:, 7]))
+    assert (np.abs(p_seq - p_pair) / p_seq).max() < 1e-15
