@@ -26,7 +26,8 @@ def pytest_collection_modifyitems(config, items):
 
 @pytest.fixture(scope="session")
 def golden():
-    path = os.path.join(ROOT, "tests", "golden", "vegas_golden.npz")
+    """Vectors computed by the UNMODIFIED reference (tests/golden/make_golden_from_reference.py)."""
+    path = os.path.join(ROOT, "tests", "golden", "reference_golden.npz")
     return dict(np.load(path))
 
 
