@@ -12,11 +12,15 @@ construction (the uniforms are generated in-kernel from the Philox counter).
 
 Workloads (BASELINE.json configs; events are PER GPU, i.e. weak scaling):
   c1  symgauss d=4,  1e6 events/iter          (configs[0])
-  c2  product  d=8,  1e7 events/iter          (configs[1], DEFAULT)
+  c2  product  d=8,  1e7 events/iter          (configs[1])
   c3  VegasFlowPlus adaptive symgauss d=8, 1e8 events/iter (configs[2], 1 GPU)
   c4dy / c4st  Drell-Yan d=4 / single-top d=3, 1e8 events/iter (configs[3])
   c5  symgauss d=20, 1.25e8 events/iter/GPU   (configs[4]: 1e9 over 8 GPUs)
-  sg8 symgauss d=8,  1e8 events/iter          (north_star target line)
+  sg8 symgauss d=8,  1e8 events/iter          (north_star target line, DEFAULT)
+
+The default line is sg8 -- the workload the north_star's ">= 50 % of fp64 peak" and ">= 7x at 8
+GPUs" targets are quoted on (it fits one GPU); the same JSON line carries a `workloads`
+sub-table with one short measurement of every other BASELINE.json config.
 
 Prints ONE JSON line on rank 0 (see the driver contract in the task statement).
 """
@@ -149,23 +153,32 @@ def cpu_best_effort(wl, sample_events):
 
 
 def run_reference_arm(args, wl):
+    """`--impl reference`: the reference's CPU path for the SAME workload, timed on the host
+    cores.  TensorFlow cannot be installed here, so this is the op-for-op reference-shaped
+    torch-CPU port (kind "port"); every step is a bounded sample of the workload -- ONE chunk of
+    MAX_EVENTS_LIMIT = 1e6 events, the unit the reference itself processes per `self.event` call
+    (monte_carlo.py:438-452, configflow.py:22) -- same K and W as the GPU arm."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     sample = min(wl["n_events"], 10**6)
-    steps = max(1, min(args.steps, 20))
-    base = cpu_reference_run(wl, steps, min(args.warmup, 1), sample)
+    steps, warmup = max(1, min(args.steps, 50)), max(1, min(args.warmup, 5))
+    base = cpu_reference_run(wl, steps, warmup, sample)
     if base is None:
         print(json.dumps({"impl": "reference", "unavailable":
                           f"no CPU restatement for workload {args.workload}"}))
         return
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT,
-        "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
         "ms_per_step": base["seconds"] / steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": wl["name"], "note": "TensorFlow is not installable here; this is "
-                   "the reference-shaped CPU restatement (oracle/ref_shaped_torch.py)"},
+        "config": {"workload": wl["name"],
+                   "sample": f"each step = one {sample}-event chunk of that workload (the "
+                             "reference's own MAX_EVENTS_LIMIT chunk); CPU throughput is "
+                             "size-independent above 1e6 events",
+                   "note": "TensorFlow is not installable here; this is the reference-shaped CPU "
+                           "restatement (oracle/ref_shaped_torch.py), all host cores"},
         "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
@@ -179,11 +192,15 @@ def run_reference_arm(args, wl):
 # ----------------------------------------------------------------------------
 def _profiled_traffic(workload):
     """DRAM bytes per event-kernel launch from the committed ncu --set full capture, or None."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-            return json.load(f).get(workload)
-    except Exception:
-        return None
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                v = json.load(f).get(workload)
+            if v is not None:
+                return v
+        except Exception:
+            pass
+    return None
 
 
 RNG_BITS = 52
@@ -192,7 +209,9 @@ RNG_BITS = 52
 def make_instance(wl, world):
     import vegasflow_b200 as vf
 
-    n_total = wl["n_events"] * (world if wl["alg"] != "plus" else 1)
+    # weak scaling: per-GPU events fixed.  VEGAS+ shards cubes: the requested total grows with
+    # the world size as well (the stratification is recomputed from it).
+    n_total = wl["n_events"] * world
     if wl["alg"] == "vegas":
         inst = vf.VegasFlow(wl["n_dim"], n_total, verbose=False, rng_bits=RNG_BITS)
     elif wl["alg"] == "plus":
@@ -205,14 +224,179 @@ def make_instance(wl, world):
     return inst
 
 
+class Bench:
+    """Shared state of the GPU arm: library handle, process group, barrier."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+
+        import __graft_entry__ as graft
+
+        graft.build()
+        from vegasflow_b200 import _lib
+
+        self.torch, self.dist, self._lib = torch, dist, _lib
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise RuntimeError("bench.py needs a CUDA device (no CPU fallback)")
+        torch.cuda.set_device(local_rank)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            import datetime
+
+            # short collective timeout: a hang must fail fast, not hold 8 GPUs for 10 minutes
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank),
+                                    timeout=datetime.timedelta(seconds=90))
+        self.lib = _lib.require_cuda()
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def agree_max(self, x):
+        """Same value on every rank (max), so loop counts derived from it cannot diverge --
+        a rank-dependent iteration count would deadlock the per-iteration collective."""
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    @staticmethod
+    def run_n(inst, n):
+        """n steps of the product path (identical count on every rank); events processed by
+        the WHOLE job (all ranks)."""
+        if n <= 0:
+            return 0
+        if inst._run_batched(n) is not None:
+            if inst._ROW == 3:  # VEGAS+: the event count changes, read it from the result rows
+                inst._after_batch(inst._fetch_rows())
+                inst._host_rows_n = 0
+                return sum(inst.events_log[-n:])
+            return inst.n_events * n
+        done = 0
+        for _ in range(n):
+            done += inst.n_events
+            inst._run_iteration()
+        return done
+
+    def run_steps(self, inst, n):
+        return self.run_n(inst, n)
+
+    def measure(self, wl, K, W, clocks=False):
+        """W warm-up steps, ~0.3 s more to ramp the clocks, then EXACTLY K timed steps
+        (barrier + synchronize on both sides, CUDA events, max over ranks), then an identical
+        K-step pass with per-kernel CUDA events for the roofline."""
+        import ctypes
+
+        torch, lib, _lib = self.torch, self.lib, self._lib
+        inst = make_instance(wl, self.world)
+        self.barrier()
+        t0 = time.perf_counter()
+        self.run_steps(inst, W)
+        self.barrier()
+        step_s = self.agree_max((time.perf_counter() - t0) / W)
+        self.run_steps(inst, int(min(2000, max(0, 0.3 / max(step_s, 1e-6)))))
+        self.barrier()
+
+        sampler = ClockSampler(torch.cuda.current_device()) if clocks else None
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev1 = torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        lib.vf_launch_count(1)
+        if sampler:
+            sampler.start()
+        ev0.record()
+        events_done = self.run_steps(inst, K)
+        ev1.record()
+        self.barrier()
+        launches = int(lib.vf_launch_count(0))
+        ms = self.agree_max(ev0.elapsed_time(ev1))  # max over ranks
+        # Second, identical K-step pass with the library's CUDA-event bracket around every
+        # event-kernel / tail-kernel launch (same stream): per-kernel durations for the
+        # roofline.  Kept out of the timed region because the event records break the
+        # programmatic-dependent-launch overlap and widen the gaps by a few microseconds.
+        lib.vf_kernel_timing(1)
+        events_pass2 = self.run_steps(inst, K)
+        self.barrier()
+        kt, kn = ctypes.c_double(0.0), ctypes.c_int(0)
+        _lib.check(lib.vf_kernel_time_ms(ctypes.byref(kt), ctypes.byref(kn)))
+        et, en = ctypes.c_double(0.0), ctypes.c_int(0)
+        _lib.check(lib.vf_epilogue_time_ms(ctypes.byref(et), ctypes.byref(en)))
+        lib.vf_kernel_timing(0)
+        kern_ms = kt.value / max(kn.value, 1)
+        epi_ms = et.value / max(en.value, 1) if en.value else None
+        clk = None
+        if sampler:
+            # keep the same steps running ~1 s more so the sampler sees the kernel under load
+            # (count derived from the agreed step time: identical on every rank)
+            if ms < 1000.0 and self.agree_max(1.0 if sampler.nv is not None else 0.0) > 0.5:
+                self.run_steps(inst, int(min(20000, 1000.0 / max(ms / K, 1e-3))))
+                self.barrier()
+            clk = sampler.stop()
+            clk["note"] = ("NVML samples every 2 ms over the timed region plus a ~1 s repeat of "
+                           "the same steps right after it" if ms < 1000.0
+                           else "NVML samples over the timed region")
+        plus = 1 if wl["alg"] == "plus" else 0
+        mode = 0 if wl["alg"] == "plain" else 1
+        iid = lib.vf_integrand_id(wl["integrand"].encode())
+        f_alg = lib.vf_flops_per_event(mode, iid, wl["n_dim"], plus)
+        per_gpu_events = events_done / K / self.world
+        per_gpu_events_pass2 = events_pass2 / K / self.world
+        achieved = per_gpu_events_pass2 * f_alg / (kern_ms * 1e-3) / 1e12
+        return dict(inst=inst, ms=ms, events_done=events_done, launches=launches,
+                    kern_ms=kern_ms, kern_n=kn.value, epi_ms=epi_ms, clocks=clk, f_alg=f_alg,
+                    per_gpu_events=per_gpu_events, achieved=achieved, plus=plus,
+                    value=events_done / (ms * 1e-3))
+
+    def measure_e2e(self, wl, K):
+        """Public API end to end: grid uploaded from PINNED host memory, run_integration(K)
+        (every iteration's (res, sigma) lands in pinned host memory, written by that
+        iteration's tail kernel), trained grid downloaded -- all inside the timed region."""
+        import numpy as np
+
+        torch = self.torch
+        inst = make_instance(wl, self.world)
+        inst.run_integration(3)  # warm-up through the same public call
+        has_grid = hasattr(inst, "load_grid")
+        host_grid = None
+        if has_grid:
+            host_grid = torch.from_numpy(
+                np.ascontiguousarray(inst.divisions.cpu().numpy())).pin_memory()
+        before = len(inst.history)
+        self.barrier()
+        t0 = time.perf_counter()
+        if has_grid:
+            inst.load_grid(numpy_grid=host_grid.numpy())  # H2D of the grid (n_dim*51*8 B)
+        inst.run_integration(K)  # public API; host receives (res, sigma) of every iteration
+        final_grid = inst.divisions.cpu() if has_grid else None  # D2H of the trained grid
+        self.barrier()
+        e2e_s = self.agree_max(time.perf_counter() - t0)
+        rows = inst.history[before:]
+        assert len(rows) == K and all(isinstance(r[0], float) for r in rows)
+        events = sum(inst.events_log[-K:]) if inst._ROW == 3 else inst.n_events * K
+        grid_bytes = host_grid.numel() * 8 if has_grid else 0
+        return dict(value=events / e2e_s, seconds=e2e_s, h2d=grid_bytes / K,
+                    d2h=8 * inst._ROW + (final_grid.numel() * 8 / K if has_grid else 0))
+
+
+TABLE_1GPU = ["c1", "c2", "c3", "c4dy", "c4st", "c5"]
+TABLE_NGPU = ["c2", "c3", "c5"]
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="sg8", choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-table", action="store_true",
+                    help="skip the per-workload sub-table (c1, c2, c3, c4dy, c4st, c5)")
     ap.add_argument("--rng-bits", type=int, default=52, choices=[52, 32],
                     help="Philox bits per uniform (52 = default stream)")
     args = ap.parse_args()
@@ -223,151 +407,43 @@ def main():
         run_reference_arm(args, wl)
         return
 
-    import torch
-    import torch.distributed as dist
-
-    import __graft_entry__ as graft
-
-    graft.build()
-    from vegasflow_b200 import _lib
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback)")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        import datetime
-
-        # short collective timeout: a hang must fail fast, not hold 8 GPUs for 10 minutes
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank),
-                                timeout=datetime.timedelta(seconds=90))
-    lib = _lib.require_cuda()
-    K, W = args.steps, max(args.warmup, 3)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # measured fp64 DFMA peak (MEASURED_PEAKS.json has no fp64 entry)
     import ctypes
 
+    B = Bench()
+    lib, _lib, world, rank = B.lib, B._lib, B.world, B.rank
+    K, W = args.steps, max(args.warmup, 3)
+
+    # measured fp64 DFMA peak (MEASURED_PEAKS.json has no fp64 entry)
     peak = ctypes.c_double(0.0)
     _lib.check(lib.vf_fp64_peak_probe(20000, ctypes.byref(peak)))
 
-    inst = make_instance(wl, world)
+    m = B.measure(wl, K, W, clocks=True)
+    e2e = B.measure_e2e(wl, K)
 
-    def run_n(n):
-        """n steps of the product path (identical count on every rank)."""
-        n_per_step = inst.n_events
-        if n <= 0:
-            return 0
-        if inst._run_batched(n) is not None:
-            return n_per_step * n
-        done = 0
-        for _ in range(n):
-            done += inst.n_events
-            inst._run_iteration()
-        return done
-
-    def agree_max(x):
-        """Same value on every rank (max), so loop counts derived from it cannot diverge --
-        a rank-dependent iteration count would deadlock the per-iteration collective."""
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    # ---- warm-up: W steps (timed to size the clock ramp), then ~0.3 s more of the same steps
-    barrier()
-    t0 = time.perf_counter()
-    run_n(W)
-    barrier()
-    step_s = agree_max((time.perf_counter() - t0) / W)
-    run_n(int(min(2000, max(0, 0.3 / max(step_s, 1e-6)))))
-    barrier()
-
-    # ---- timed region: exactly K steps of the product path, device-timed, max over ranks.
-    # Single rank: ONE vf_run_iterations call enqueues all K iterations (2 launches each).
-    # Multi rank: per iteration vf_run_event, the NCCL all-reduce, vf_iteration_epilogue.
-    sampler = ClockSampler(torch.cuda.current_device())
-    ev0 = torch.cuda.Event(enable_timing=True)
-    ev1 = torch.cuda.Event(enable_timing=True)
-    def run_steps():
-        return run_n(K)
-
-    barrier()
-    lib.vf_launch_count(1)
-    sampler.start()
-    ev0.record()
-    events_done = run_steps()
-    ev1.record()
-    barrier()
-    launches = int(lib.vf_launch_count(0))
-    ms = agree_max(ev0.elapsed_time(ev1))  # max over ranks
-    value = events_done / (ms * 1e-3)
-    # Second, identical K-step pass with the library's CUDA-event bracket around every
-    # event-kernel / epilogue launch (same stream): per-kernel durations for the roofline.
-    # Kept out of the timed region above because the extra event records widen the gaps
-    # between the back-to-back launches by a few microseconds.
-    lib.vf_kernel_timing(1)
-    run_steps()
-    barrier()
-    kt, kn = ctypes.c_double(0.0), ctypes.c_int(0)
-    _lib.check(lib.vf_kernel_time_ms(ctypes.byref(kt), ctypes.byref(kn)))
-    et, en = ctypes.c_double(0.0), ctypes.c_int(0)
-    _lib.check(lib.vf_epilogue_time_ms(ctypes.byref(et), ctypes.byref(en)))
-    lib.vf_kernel_timing(0)
-    kern_ms = kt.value / max(kn.value, 1)
-    epi_ms = et.value / max(en.value, 1) if en.value else None
-    # keep the same steps running ~1 s more so the clock sampler sees the kernel under load
-    # (count derived from the agreed step time: identical on every rank)
-    if ms < 1000.0 and agree_max(1.0 if sampler.nv is not None else 0.0) > 0.5:
-        run_n(int(min(20000, 1000.0 / max(ms / K, 1e-3))))
-        barrier()
-    clocks = sampler.stop()
-    clocks["note"] = ("NVML samples every 2 ms over the timed region plus a ~1 s repeat of the same "
-                      "steps right after it" if ms < 1000.0 else "NVML samples over the timed region")
-
-    # ---- e2e: public API, one D2H read of (res, sigma) per step like the reference's logging
-    inst2 = make_instance(wl, world)
-    import numpy as np
-
-    host_grid = np.ascontiguousarray(inst2.divisions.cpu().numpy())
-    for _ in range(3):
-        inst2.run_iteration()
-    barrier()
-    e2e_events = 0
-    t0 = time.perf_counter()
-    inst2.load_grid(numpy_grid=host_grid)  # H2D of the grid (n_dim*51*8 B)
-    for _ in range(K):
-        e2e_events += inst2.n_events
-        inst2.run_iteration()  # public API: one 16-byte D2H read + sync, every step
-    final_grid = inst2.divisions.cpu()  # D2H of the trained grid
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
-    grid_bytes = host_grid.nbytes
+    # ---- every BASELINE.json config as a short line of its own (same protocol, fewer steps)
+    table = {}
+    if not args.no_table:
+        for name in (TABLE_1GPU if world == 1 else TABLE_NGPU):
+            if name == args.workload:
+                continue
+            t = B.measure(WORKLOADS[name], min(K, 10), 3)
+            table[name] = {
+                "workload": WORKLOADS[name]["name"], "value": t["value"], "unit": UNIT,
+                "steps": min(K, 10), "ms_per_step": t["ms"] / min(K, 10),
+                "events_per_step_per_gpu": t["per_gpu_events"],
+                "kernel_ms": t["kern_ms"], "epilogue_kernel_ms": t["epi_ms"],
+                "flops_per_event": t["f_alg"], "achieved_tflops": t["achieved"],
+                "frac": t["achieved"] / peak.value,
+            }
 
     if rank == 0:
-        plus = 1 if wl["alg"] == "plus" else 0
-        mode = 0 if wl["alg"] == "plain" else 1
-        iid = lib.vf_integrand_id(wl["integrand"].encode())
-        f_alg = lib.vf_flops_per_event(mode, iid, wl["n_dim"], plus)
-        per_gpu_events = events_done / K / (world if wl["alg"] != "plus" else 1)
-        achieved = per_gpu_events * f_alg / (kern_ms * 1e-3) / 1e12
+        inst = m["inst"]
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
-            "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
+            "metric": METRIC, "value": m["value"], "unit": UNIT, "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": m["ms"] / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
-                "workload": wl["name"], "events_per_step_per_gpu": per_gpu_events,
+                "workload": wl["name"], "events_per_step_per_gpu": m["per_gpu_events"],
                 "train": True, "rng": f"philox4x32-10, {RNG_BITS}-bit uniforms, generated in-kernel",
                 "collective": ("none (1 GPU)" if world == 1 else
                                "fused block-reduce + NVLink peer-memory all-reduce + refine kernel"
@@ -377,26 +453,30 @@ def main():
                       " grid + partials are <1 MB",
             },
             "roofline": {
-                "bound": "fp64", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
-                "frac": achieved / peak.value, "traffic": _profiled_traffic(args.workload),
+                "bound": "fp64", "achieved": m["achieved"], "peak": peak.value, "unit": "TFLOP/s",
+                "frac": m["achieved"] / peak.value, "traffic": _profiled_traffic(args.workload),
                 "peak_source": "DFMA-chain probe run in this process (MEASURED_PEAKS.json has no "
                                "fp64 entry)",
-                "peak_nominal": FP64_NOMINAL_TFLOPS, "frac_of_nominal": achieved / FP64_NOMINAL_TFLOPS,
-                "flops_per_event": f_alg,
-                "kernel": "plus_event_kernel" if plus else "event_kernel",
-                "kernel_ms": kern_ms, "kernel_launches_timed": kn.value,
+                "peak_nominal": FP64_NOMINAL_TFLOPS,
+                "frac_of_nominal": m["achieved"] / FP64_NOMINAL_TFLOPS,
+                "flops_per_event": m["f_alg"],
+                "kernel": "plus_event_kernel" if m["plus"] else "event_kernel",
+                "kernel_ms": m["kern_ms"], "kernel_launches_timed": m["kern_n"],
                 "kernel_timing": "CUDA events around each launch on its stream, over an identical "
                                  "K-step pass run immediately after the timed region",
-                "kernel_share_of_step": kern_ms / (ms / K),
-                "epilogue_kernel_ms": epi_ms,
+                "kernel_share_of_step": m["kern_ms"] / (m["ms"] / K),
+                "epilogue_kernel_ms": m["epi_ms"],
             },
-            "clocks": clocks,
-            "e2e": {"value": e2e_events / e2e_s, "unit": UNIT,
-                    "h2d_bytes_per_step": grid_bytes / K,
-                    "d2h_bytes_per_step": 16 + final_grid.numel() * 8 / K,
-                    "note": "VegasFlow public API: grid uploaded from host, (res, sigma) read back "
-                            "to the host after every iteration, trained grid downloaded at the end"},
-            "gpu_launches": launches,
+            "clocks": m["clocks"],
+            "e2e": {"value": e2e["value"], "unit": UNIT,
+                    "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
+                    "note": "public API: grid uploaded from pinned host memory, "
+                            "run_integration(K) with (res, sigma) of EVERY iteration delivered to "
+                            "pinned host memory by that iteration's tail kernel, trained grid "
+                            "downloaded; per-step inputs are the Philox (seed, iteration) launch "
+                            "parameters -- the path has no per-event host data by construction"},
+            "gpu_launches": m["launches"],
+            "workloads": table,
         }
         if world == 1 and not args.no_cpu_baseline:
             base = cpu_reference_run(wl, 3, 1, min(wl["n_events"], 10**6))
@@ -408,7 +488,7 @@ def main():
                     line["cpu_best_effort"] = best
         print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        B.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -39,7 +39,7 @@ extern "C" {
 #endif
 
 #define VF_BINS_MAX 50
-#define VF_ABI_VERSION 1
+#define VF_ABI_VERSION 2
 
 /* sampling modes */
 #define VF_MODE_PLAIN 0 /* PlainFlow, src/vegasflow/plain.py:18-35 */
@@ -141,21 +141,27 @@ int vf_iteration_epilogue(int n_dim, int64_t n_events, int train, const double* 
  * Iteration k uses Philox stream `first_iteration + k` and xjac = 1/n_events.
  * results[k] = (res_k, sigma_k); packed = [hist n_dim*50 | sum wf | sum (wf)^2] of the last
  * iteration; divisions is refined in place when train != 0.  The inverse-variance
- * combination (monte_carlo.py:713-732) stays with the caller.
+ * combination (monte_carlo.py:713-732) stays with the caller.  When host_results is not NULL
+ * (page-locked host memory) row k is also copied there asynchronously right after iteration k
+ * by the iteration's tail kernel (stores through the device alias of the mapped host memory)
+ * -- the reference's per-iteration read-back for logging (monte_carlo.py:699-710) without a
+ * host synchronisation; the rows are valid once the stream has been synchronised.
  */
 int vf_run_iterations(int mode, int integrand, int n_dim, int64_t n_events, uint64_t seed,
                       uint32_t first_iteration, int n_iter, int train,
                       double* divisions /*[dev] in/out, NULL for PLAIN*/,
                       const double* xmin /*[host]*/, const double* xdelta /*[host]*/,
                       double* packed /*[dev] [n_dim*50+2]*/, double* results /*[dev] [n_iter][2]*/,
+                      double* host_results /*[host, pinned] [n_iter][2] or NULL*/,
                       void* workspace /*[dev]*/, size_t workspace_bytes, void* stream);
 
 /*
  * n_iter iterations of one rank of a multi-GPU run, each fused with its collective: the event
  * kernel over this rank's events [ev_begin, ev_begin + n_events_local), then ONE kernel that reduces
  * the block partials, exchanges the [n_dim*50+2] sums with all peers by P2P stores over
- * NVLink (one-shot all-reduce on peer-mapped memory, flags with release/acquire at system
- * scope), adds the `world` contributions in rank order, computes (res, sigma) and refines the
+ * NVLink (one-shot all-reduce on peer-mapped memory; every 16-byte store carries the value and
+ * the exchange sequence number, so the data is its own arrival flag: no fence, no flag hop),
+ * adds the `world` contributions in rank order, computes (res, sigma) and refines the
  * grid -- every rank ends with bit-identical divisions.  Replaces the joblib device pool and
  * host-side _accumulate of the reference (monte_carlo.py:143-157, 318-365, 454-480, 72-92).
  * peer_buffers: [host] `world` device addresses of every rank's exchange buffer of
@@ -164,14 +170,15 @@ int vf_run_iterations(int mode, int integrand, int n_dim, int64_t n_events, uint
  * at 1 and advance by one per iteration, identically on every rank.  world <= 8.
  * results[k] = (res_k, sigma_k).
  */
-size_t vf_exchange_bytes(int n_dim, int world);
+size_t vf_exchange_bytes(int n_dim, int world, int64_t n_cubes /*0 unless VEGAS+*/);
 int vf_run_iterations_sharded(int mode, int integrand, int n_dim, uint64_t ev_begin,
                               int64_t n_events_local, int64_t n_events_total, uint64_t seed,
                               uint32_t first_iteration, int n_iter, int train,
                               double* divisions /*[dev]*/, const double* xmin /*[host]*/,
                               const double* xdelta /*[host]*/, double* packed /*[dev] [n_dim*50+2]*/,
-                              double* results /*[dev] [n_iter][2]*/, void* workspace /*[dev]*/,
-                              size_t workspace_bytes, int rank, int world,
+                              double* results /*[dev] [n_iter][2]*/,
+                              double* host_results /*[host, pinned] or NULL*/,
+                              void* workspace /*[dev]*/, size_t workspace_bytes, int rank, int world,
                               const uint64_t* peer_buffers /*[host] [world]*/, uint64_t first_seq,
                               void* stream);
 
@@ -254,6 +261,38 @@ int vfp_iteration_epilogue(int64_t n_cubes, const double* ress /*[dev]*/,
                            int64_t* ev_offset /*[dev] out*/, double* arr_var /*[dev] out*/,
                            double* result /*[dev] [2]*/, int64_t* n_events_out /*[dev]*/,
                            void* stream);
+
+/*
+ * n_iter whole VEGAS+ iterations with the sample allocation RESIDENT ON THE DEVICE: per
+ * iteration the stratified event kernel (event count read from ev_offset[n_cubes] on the
+ * device) and ONE tail kernel doing histogram reduction + grid refinement (vflow.py:349-362),
+ * arr_var, (res, sigma) (vflowplus.py:216-233), redistribute_samples + new offsets
+ * (vflowplus.py:153-163) and the zeroing of the per-cube sums -- no host synchronisation and no
+ * host copy of n_events between iterations.  Replaces VegasFlowPlus._iteration_content
+ * (vflowplus.py:222-242) inside the loop of run_integration (monte_carlo.py:679-685), including
+ * the `n_events` setter + recompile of the reference (monte_carlo.py:187-193).
+ * results[k] = (res_k, sigma_k, n_events of iteration k+1); host_results as vf_run_iterations.
+ * ress / ress2 must be zero on entry and are zero on exit; xjac = 1/n_cubes (vflowplus.py:139).
+ * world > 1 (the reference is single-device, vflowplus.py:88-100): rank r evaluates
+ * the events of a contiguous cube range balanced on the event prefix sum; the tail kernel
+ * all-reduces the histogram and the partial (res, sigma^2) and all-gathers the per-cube
+ * variances through the peer buffers (vf_exchange_bytes(n_dim, world, n_cubes) bytes each,
+ * zero-initialised), then every rank redistributes redundantly: n_ev stays bit-identical.
+ */
+int vfp_run_iterations(int integrand, int n_dim, int n_strat, int64_t n_cubes, uint64_t seed,
+                       uint32_t first_iteration, int n_iter, int rng_bits /*52 | 32*/, int train,
+                       int adaptive, int min_neval_hcube, int64_t init_calls,
+                       double* divisions /*[dev] in/out*/, const double* xmin /*[host]*/,
+                       const double* xdelta /*[host]*/, int32_t* n_ev /*[dev] in/out*/,
+                       int64_t* ev_offset /*[dev] in/out [n_cubes+1]*/,
+                       double* ress /*[dev] [n_cubes]*/, double* ress2 /*[dev] [n_cubes]*/,
+                       double* arr_var /*[dev] out [n_cubes]*/,
+                       double* out_hist /*[dev] [n_dim][50]*/,
+                       double* results /*[dev] [n_iter][3]*/,
+                       double* host_results /*[host, pinned] [n_iter][3] or NULL*/,
+                       void* workspace /*[dev]*/, size_t workspace_bytes, int rank, int world,
+                       const uint64_t* peer_buffers /*[host] [world] or NULL*/, uint64_t first_seq,
+                       void* stream);
 
 /* ------------------------------------------------------------------------
  * Measurement helpers (no reference counterpart)

@@ -1,4 +1,7 @@
-"""Run under torchrun (2+ ranks, NCCL): sharded VegasFlow integration; rank 0 writes the result.
+"""Run under torchrun (2+ ranks, NCCL): sharded integration; rank 0 writes the result.
+
+    dist_check.py <out.json> [vegas|plus|plain]
+
 Used by tests/test_api_gpu.py::test_two_gpu_sharding_matches_single_gpu."""
 import json
 import os
@@ -11,23 +14,41 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import vegasflow_b200 as vf  # noqa: E402
 
 
+def make(alg):
+    if alg == "plus":
+        return vf.VegasFlowPlus(4, 400000, adaptive=True, verbose=False)
+    if alg == "plain":
+        return vf.PlainFlow(4, 400000, verbose=False)
+    return vf.VegasFlow(4, 400000, verbose=False)
+
+
 def main():
+    alg = sys.argv[2] if len(sys.argv) > 2 else "vegas"
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    inst = vf.VegasFlow(4, 400000, verbose=False)
+    inst = make(alg)
     inst.set_seed(2718)
     inst.compile(vf.integrands.symgauss)
     res, err = inst.run_integration(4)
-    grid = inst.divisions.cpu().numpy()
-    # every rank must hold the identical refined grid
-    g = inst.divisions.clone()
-    dist.broadcast(g, src=0)
-    assert torch.equal(g, inst.divisions), "ranks diverged"
+    out = {"res": res, "err": err, "exchange": "p2p" if inst._exchange is not None else "nccl",
+           "history": [[h[0], h[1]] for h in inst.history]}
+    if alg != "plain":
+        # every rank must hold the identical refined grid
+        g = inst.divisions.clone()
+        dist.broadcast(g, src=0)
+        assert torch.equal(g, inst.divisions), "ranks diverged (grid)"
+        out["grid"] = inst.divisions.cpu().numpy().tolist()
+    if alg == "plus":
+        n_ev = inst.n_ev.clone()
+        dist.broadcast(n_ev, src=0)
+        assert torch.equal(n_ev, inst.n_ev), "ranks diverged (n_ev)"
+        out["n_ev"] = inst.n_ev.cpu().numpy().tolist()
+        out["n_events"] = inst.n_events
+        out["events_log"] = inst.events_log
     if dist.get_rank() == 0:
         with open(sys.argv[1], "w") as f:
-            json.dump({"res": res, "err": err, "grid": grid.tolist(),
-                       "exchange": "p2p" if inst._exchange is not None else "nccl"}, f)
+            json.dump(out, f)
     dist.destroy_process_group()
 
 

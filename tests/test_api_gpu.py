@@ -339,16 +339,26 @@ def test_batched_and_verbose_paths_agree():
     assert abs(out[0][1] - out[1][1]) <= 1e-7 * out[0][1]
 
 
-def test_two_gpu_sharding_matches_single_gpu(tmp_path):
-    """torchrun with 2 ranks over NCCL: same seed -> same integral as one rank (SURVEY 8e)."""
+def _torchrun_dist_check(tmp_path, tag, alg, exchange, port):
+    import json
     import os
     import subprocess
     import sys
 
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     script = os.path.join(root, "tests", "dist_check.py")
+    out = tmp_path / f"dist_{tag}.json"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), script, str(out), alg]
+    env = dict(os.environ, VEGASFLOW_B200_EXCHANGE=exchange)
+    subprocess.run(cmd, check=True, timeout=600, cwd=root, env=env)
+    return json.load(open(out))
+
+
+def test_two_gpu_sharding_matches_single_gpu(tmp_path):
+    """torchrun with 2 ranks over NCCL: same seed -> same integral as one rank (SURVEY 8e)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
     inst = VegasFlow(4, 400000, verbose=False)
     inst.set_seed(2718)
     inst.compile(vf.integrands.symgauss)
@@ -356,16 +366,38 @@ def test_two_gpu_sharding_matches_single_gpu(tmp_path):
     grid = inst.divisions.cpu().numpy()
     # both collectives: the fused NVLink peer-memory kernel and the NCCL all-reduce path
     for k, exchange in enumerate(("p2p", "nccl")):
-        out = tmp_path / f"dist_{exchange}.json"
-        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-               "--master-addr", "127.0.0.1", "--master-port", str(29611 + k), script, str(out)]
-        env = dict(os.environ, VEGASFLOW_B200_EXCHANGE=exchange)
-        subprocess.run(cmd, check=True, timeout=600, cwd=root, env=env)
-        data = json.load(open(out))
+        data = _torchrun_dist_check(tmp_path, exchange, "vegas", exchange, 29611 + k)
         assert data["exchange"] == exchange
         assert abs(res - data["res"]) <= 1e-9 * abs(res)
         assert abs(err - data["err"]) <= 1e-7 * err
         np.testing.assert_allclose(grid, np.array(data["grid"]), atol=1e-11)
+    # PlainFlow shards the same way (no grid, two sums)
+    inst = PlainFlow(4, 400000, verbose=False)
+    inst.set_seed(2718)
+    inst.compile(vf.integrands.symgauss)
+    res, err = inst.run_integration(4)
+    data = _torchrun_dist_check(tmp_path, "plain", "plain", "p2p", 29615)
+    assert abs(res - data["res"]) <= 1e-9 * abs(res) and abs(err - data["err"]) <= 1e-7 * err
+
+
+def test_two_gpu_vegasflowplus_cube_sharding_matches_single_gpu(tmp_path):
+    """VEGAS+ over 2 ranks -- contiguous cube ranges balanced on the event
+    prefix sum, all-reduce of the histogram and the partial (res, sigma^2), all-gather of the
+    per-cube variances, redundant redistribute_samples.  Must equal the 1-rank run: the Philox
+    counters are global event indices, so only the summation order differs."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    inst = VegasFlowPlus(4, 400000, adaptive=True, verbose=False)
+    inst.set_seed(2718)
+    inst.compile(vf.integrands.symgauss)
+    res, err = inst.run_integration(4)
+    data = _torchrun_dist_check(tmp_path, "plus", "plus", "p2p", 29617)
+    assert data["exchange"] == "p2p"
+    assert abs(res - data["res"]) <= 1e-9 * abs(res)
+    assert abs(err - data["err"]) <= 1e-7 * err
+    np.testing.assert_allclose(inst.divisions.cpu().numpy(), np.array(data["grid"]), atol=1e-11)
+    assert data["events_log"] == inst.events_log and data["n_events"] == inst.n_events
+    np.testing.assert_array_equal(inst.n_ev.cpu().numpy(), np.array(data["n_ev"]))
 
 
 @pytest.mark.parametrize("alg", [PlainFlow, VegasFlow, VegasFlowPlus])

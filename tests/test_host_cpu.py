@@ -38,7 +38,7 @@ def test_abi_exports_every_declared_symbol():
 
 def test_abi_host_only_entry_points():
     lib = _lib.load()
-    assert lib.vf_version() == 1
+    assert lib.vf_version() == 2
     assert lib.vf_integrand_id(b"symgauss") == 0
     assert lib.vf_integrand_id(b"product") == 1
     assert lib.vf_integrand_id(b"drellyan_lo") == 2

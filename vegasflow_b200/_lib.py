@@ -28,12 +28,12 @@ _SIGNATURES = {
                                C.c_uint64, C.c_uint32, C.c_int, _P, _P, _P, _P, _P, C.c_int, _P,
                                C.c_size_t, _P]),
     "vf_run_iterations": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_uint64, C.c_uint32,
-                                    C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
-    "vf_exchange_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+                                    C.c_int, C.c_int, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+    "vf_exchange_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int64]),
     "vf_run_iterations_sharded": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_int64,
                                             C.c_int64, C.c_uint64, C.c_uint32, C.c_int, C.c_int,
-                                            _P, _P, _P, _P, _P, _P, C.c_size_t, C.c_int, C.c_int,
-                                            C.POINTER(C.c_uint64), C.c_uint64, _P]),
+                                            _P, _P, _P, _P, _P, _P, _P, C.c_size_t, C.c_int,
+                                            C.c_int, C.POINTER(C.c_uint64), C.c_uint64, _P]),
     "vf_refine_grid": (C.c_int, [C.c_int, _P, _P, _P]),
     "vf_iteration_epilogue": (C.c_int, [C.c_int, C.c_int64, C.c_int, _P, _P, _P, _P, _P]),
     "vf_digest_from_uniforms": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, _P, _P, C.c_double,
@@ -50,6 +50,10 @@ _SIGNATURES = {
                                 _P, C.c_int, _P, C.c_size_t, _P, _P, _P, _P, _P, _P]),
     "vfp_iteration_epilogue": (C.c_int, [C.c_int64, _P, _P, C.c_int, C.c_int, C.c_int64, _P, _P,
                                          _P, _P, _P, _P]),
+    "vfp_run_iterations": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_uint64, C.c_uint32,
+                                     C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64, _P, _P,
+                                     _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, C.c_int,
+                                     C.c_int, C.POINTER(C.c_uint64), C.c_uint64, _P]),
     "vf_fp64_peak_probe": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     "vf_kernel_timing": (C.c_int, [C.c_int]),
     "vf_kernel_time_ms": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int)]),

@@ -118,6 +118,24 @@ static inline int check_rng_bits(int rng_bits) {
     return VF_ERR_INVALID;
 }
 
+// Device alias of the caller's page-locked result ring: the tail kernel of every iteration
+// stores (res, sigma) straight into it (posted writes over PCIe/C2C) -- the per-iteration
+// device->host read-back of the reference's logging (monte_carlo.py:699-710) without a memcpy
+// node between the kernels and without a host synchronisation per iteration.
+static int map_host_results(double* host_results, double** dev_alias) {
+    *dev_alias = nullptr;
+    if (!host_results) return VF_OK;
+    void* d = nullptr;
+    if (cudaHostGetDevicePointer(&d, host_results, 0) != cudaSuccess || !d) {
+        (void)cudaGetLastError();
+        set_error("host_results must be page-locked, device-mapped host memory "
+                  "(cudaHostAlloc / torch pin_memory)");
+        return VF_ERR_INVALID;
+    }
+    *dev_alias = (double*)d;
+    return VF_OK;
+}
+
 static int check_common(int n_dim, int64_t n) {
     if (n_dim < 1) {
         set_error("n_dim must be >= 1 (got %d)", n_dim);
@@ -327,7 +345,8 @@ int vf_run_event(int mode, int integrand, int n_dim, uint64_t ev_begin, int64_t 
 int vf_run_iterations(int mode, int integrand, int n_dim, int64_t n_events, uint64_t seed,
                       uint32_t first_iteration, int n_iter, int train, double* divisions,
                       const double* xmin, const double* xdelta, double* packed, double* results,
-                      void* workspace, size_t workspace_bytes, void* stream) {
+                      double* host_results, void* workspace, size_t workspace_bytes,
+                      void* stream) {
     int rc = check_common(n_dim, n_events);
     if (rc) return rc;
     const int rng_bits = split_mode(mode);
@@ -364,29 +383,32 @@ int vf_run_iterations(int mode, int integrand, int n_dim, int64_t n_events, uint
     L.k.train = train;
     double* out_hist = packed;
     double* out_sums = packed + (size_t)n_dim * kBins;
+    double* host_alias = nullptr;
+    rc = map_host_results(host_results, &host_alias);
+    if (rc) return rc;
     for (int it = 0; it < n_iter; ++it) {
         L.k.iteration = first_iteration + (uint32_t)it;
         rc = do_launch_event(integrand, L);
         if (rc) return rc;
         rc = launch_finalize_epilogue((double*)workspace, nblocks, n_dim, with_hist, n_events,
                                       train, out_sums, out_hist, divisions, results + 2 * it,
-                                      L.stream);
+                                      host_alias ? host_alias + 2 * it : nullptr, L.stream);
         if (rc) return rc;
     }
     return VF_OK;
 }
 
-size_t vf_exchange_bytes(int n_dim, int world) {
-    return (n_dim < 1 || world < 1) ? 0 : exchange_bytes(n_dim, world);
+size_t vf_exchange_bytes(int n_dim, int world, int64_t n_cubes) {
+    return (n_dim < 1 || world < 1 || n_cubes < 0) ? 0 : exchange_bytes(n_dim, world, n_cubes);
 }
 
 int vf_run_iterations_sharded(int mode, int integrand, int n_dim, uint64_t ev_begin,
                               int64_t n_events_local, int64_t n_events_total, uint64_t seed,
                               uint32_t first_iteration, int n_iter, int train, double* divisions,
                               const double* xmin, const double* xdelta, double* packed,
-                              double* results, void* workspace, size_t workspace_bytes, int rank,
-                              int world, const uint64_t* peer_buffers, uint64_t first_seq,
-                              void* stream) {
+                              double* results, double* host_results, void* workspace,
+                              size_t workspace_bytes, int rank, int world,
+                              const uint64_t* peer_buffers, uint64_t first_seq, void* stream) {
     double* result = results;
     const uint64_t seq = first_seq;
     int rc = check_common(n_dim, n_events_local);
@@ -427,14 +449,18 @@ int vf_run_iterations_sharded(int mode, int integrand, int n_dim, uint64_t ev_be
     PeerPtrs peers;
     for (int p = 0; p < kMaxWorld; ++p)
         peers.base[p] = p < world ? (unsigned long long*)(uintptr_t)peer_buffers[p] : nullptr;
+    double* host_alias = nullptr;
+    rc = map_host_results(host_results, &host_alias);
+    if (rc) return rc;
     for (int it = 0; it < n_iter; ++it) {
         L.k.iteration = first_iteration + (uint32_t)it;
         rc = do_launch_event(integrand, L);
         if (rc) return rc;
         rc = launch_exchange_epilogue((double*)workspace, nblocks, n_dim, with_hist,
                                       n_events_total, train, packed + (size_t)n_dim * kBins, packed,
-                                      divisions, result + 2 * it, rank, world, peers, seq + it,
-                                      L.stream);
+                                      divisions, result + 2 * it,
+                                      host_alias ? host_alias + 2 * it : nullptr, rank, world,
+                                      peers, seq + it, L.stream);
         if (rc) return rc;
     }
     return VF_OK;
@@ -587,6 +613,8 @@ int vfp_run_event(int integrand, int n_dim, int n_strat, int64_t n_cubes, int64_
     L.k.n_cubes = n_cubes;
     L.k.n_events = n_events;
     L.k.n_strat = n_strat;
+    L.k.rank = 0;
+    L.k.world = 1;
     L.k.xjac = xjac;
     L.k.pk = make_philox_keys(seed);
     L.k.iteration = iteration;
@@ -611,6 +639,76 @@ int vfp_iteration_epilogue(int64_t n_cubes, const double* ress, const double* re
     }
     return launch_plus_epilogue(n_cubes, ress, ress2, adaptive, min_neval_hcube, init_calls, n_ev,
                                 ev_offset, arr_var, result, n_events_out, (cudaStream_t)stream);
+}
+
+int vfp_run_iterations(int integrand, int n_dim, int n_strat, int64_t n_cubes, uint64_t seed,
+                       uint32_t first_iteration, int n_iter, int rng_bits, int train, int adaptive,
+                       int min_neval_hcube, int64_t init_calls, double* divisions,
+                       const double* xmin, const double* xdelta, int32_t* n_ev,
+                       int64_t* ev_offset, double* ress, double* ress2, double* arr_var,
+                       double* out_hist, double* results, double* host_results, void* workspace,
+                       size_t workspace_bytes, int rank, int world, const uint64_t* peer_buffers,
+                       uint64_t first_seq, void* stream) {
+    int rc = check_common(n_dim, 0);
+    if (rc) return rc;
+    rc = check_rng_bits(rng_bits);
+    if (rc) return rc;
+    if (n_iter < 0 || n_strat < 1 || n_cubes < 1 || !divisions || !n_ev || !ev_offset || !ress ||
+        !ress2 || !arr_var || !results || !workspace || (train && !out_hist) || world < 1 ||
+        world > kMaxWorld || rank < 0 || rank >= world ||
+        (world > 1 && (!peer_buffers || first_seq == 0))) {
+        set_error("vfp_run_iterations: bad arguments (world must be 1..%d)", kMaxWorld);
+        return VF_ERR_INVALID;
+    }
+    if (workspace_bytes < workspace_need(n_dim)) {
+        set_error("workspace too small: %zu < %zu", workspace_bytes, workspace_need(n_dim));
+        return VF_ERR_WORKSPACE;
+    }
+    PlusLaunch L;
+    L.n_dim = n_dim;
+    L.rng_bits = rng_bits;
+    L.stream = (cudaStream_t)stream;
+    int nblocks = 0;
+    L.nblocks_out = &nblocks;
+    rc = make_limits(n_dim, xmin, xdelta, &L.k.lim);
+    if (rc) return rc;
+    fill_consts(integrand, n_dim, &L.k.ic);
+    L.k.divisions = divisions;
+    L.k.partials = (double*)workspace;
+    L.k.n_ev = n_ev;
+    L.k.ev_offset = ev_offset;
+    L.k.ress = ress;
+    L.k.ress2 = ress2;
+    L.k.rnds = nullptr;
+    L.k.x = L.k.w = L.k.wf = nullptr;
+    L.k.ind = nullptr;
+    L.k.n_cubes = n_cubes;
+    L.k.n_events = -1;  // device-resident: ev_offset[n_cubes]
+    L.k.n_strat = n_strat;
+    L.k.rank = rank;
+    L.k.world = world;
+    L.k.xjac = 1.0 / (double)n_cubes;  // vflowplus.py:139
+    L.k.pk = make_philox_keys(seed);
+    L.k.train = train;
+    PeerPtrs peers;
+    for (int p = 0; p < kMaxWorld; ++p)
+        peers.base[p] = (world > 1 && p < world) ? (unsigned long long*)(uintptr_t)peer_buffers[p]
+                                                 : nullptr;
+    double* host_alias = nullptr;
+    rc = map_host_results(host_results, &host_alias);
+    if (rc) return rc;
+    for (int it = 0; it < n_iter; ++it) {
+        L.k.iteration = first_iteration + (uint32_t)it;
+        rc = do_launch_plus(integrand, L);
+        if (rc) return rc;
+        rc = launch_plus_iteration_tail((double*)workspace, nblocks, n_dim, train, out_hist,
+                                        divisions, n_cubes, ress, ress2, adaptive, min_neval_hcube,
+                                        init_calls, n_ev, ev_offset, arr_var, results + 3 * it,
+                                        host_alias ? host_alias + 3 * it : nullptr, rank, world,
+                                        peers, first_seq + it, L.stream);
+        if (rc) return rc;
+    }
+    return VF_OK;
 }
 
 int vf_fp64_peak_probe(int iters, double* tflops) {

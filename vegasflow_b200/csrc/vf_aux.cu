@@ -2,11 +2,29 @@
 // per-block partials, grid refinement, iteration epilogues, the unfused
 // sample/accumulate pair, and the fp64 peak probe.
 // Reference citations are file:line relative to /root/reference.
+#include <cstdlib>
+
 #include "vf_aux.cuh"
 
 namespace vf {
 
 __host__ __device__ inline int64_t imin64(int64_t a, int64_t b) { return a < b ? a : b; }
+
+// Bound on every peer-exchange wait (VEGASFLOW_B200_EXCHANGE_TIMEOUT_S, default 60 s): long
+// enough for host-side skew between ranks (rank-0-only I/O between calls), short enough that a
+// crashed peer does not hold the GPU.
+static unsigned long long exchange_timeout_ns() {
+    static unsigned long long cached = 0;
+    if (cached == 0) {
+        double sec = 60.0;
+        if (const char* env = getenv("VEGASFLOW_B200_EXCHANGE_TIMEOUT_S")) {
+            const double v = atof(env);
+            if (v > 0.0) sec = v;
+        }
+        cached = (unsigned long long)(sec * 1e9);
+    }
+    return cached;
+}
 
 // ---------------------------------------------------------------------------
 // Gather of one iteration's sums from the workspace (vf_common.cuh layout) by a 128-thread
@@ -223,9 +241,12 @@ __global__ void __launch_bounds__(64) epilogue_kernel(int n_dim, double n_events
 // two scalars in a fixed order and writes (res, sigma).
 __global__ void __launch_bounds__(kFinThreads) finalize_epilogue_kernel(
     double* __restrict__ workspace, int nblocks, int n_dim, int with_hist, double n_events,
-    int train, double* out_sums, double* out_hist, double* divisions, double* result) {
+    int train, double* out_sums, double* out_hist, double* divisions, double* result,
+    double* result_host) {
     __shared__ double part[kFinThreads / 2][2];
     __shared__ double row[64];
+    pdl_launch_dependents();  // the next event kernel may get resident; it waits for this grid
+    pdl_wait();               // the event kernel's records and accumulator are complete
     VF_PHASE(0);
     const bool scalars = (int)blockIdx.x == (with_hist ? n_dim : 0);
     const int blk = scalars ? n_dim : (int)blockIdx.x;
@@ -240,8 +261,13 @@ __global__ void __launch_bounds__(kFinThreads) finalize_epilogue_kernel(
             const double res = row[0], res2 = row[1];
             const double err_tmp2 = __ddiv_rn(
                 __dsub_rn(__dmul_rn(n_events, res2), __dmul_rn(res, res)), n_events - 1.0);
+            const double sigma = sqrt(fmax(err_tmp2, 0.0));
             result[0] = res;
-            result[1] = sqrt(fmax(err_tmp2, 0.0));
+            result[1] = sigma;
+            if (result_host) {  // mapped pinned host memory: posted stores, no memcpy node
+                result_host[0] = res;
+                result_host[1] = sigma;
+            }
         }
         return;
     }
@@ -256,15 +282,15 @@ __global__ void __launch_bounds__(kFinThreads) finalize_epilogue_kernel(
 
 int launch_finalize_epilogue(double* partials, int nblocks, int n_dim, bool with_hist,
                              int64_t n_events, int train, double* out_sums, double* out_hist,
-                             double* divisions, double* result, cudaStream_t stream) {
+                             double* divisions, double* result, double* result_host,
+                             cudaStream_t stream) {
     const int blocks = with_hist ? n_dim + 1 : 1;
     timing_begin(stream, 1);
-    finalize_epilogue_kernel<<<blocks, kFinThreads, 0, stream>>>(
-        partials, nblocks, n_dim, with_hist ? 1 : 0, (double)n_events, train, out_sums, out_hist,
-        divisions, result);
+    VF_CUDA_CHECK(launch_pdl(finalize_epilogue_kernel, blocks, kFinThreads, 0, stream, partials,
+                             nblocks, n_dim, with_hist ? 1 : 0, (double)n_events, train, out_sums,
+                             out_hist, divisions, result, result_host));
     timing_end(stream, 1);
     count_launch();
-    VF_CUDA_CHECK(cudaGetLastError());
     return VF_OK;
 }
 
@@ -272,77 +298,142 @@ int launch_finalize_epilogue(double* partials, int nblocks, int n_dim, bool with
 // Multi-GPU: block reduction + one-shot all-reduce over NVLink peer memory + sigma + refine in
 // ONE kernel (replaces finalize_kernel -> ncclAllReduce -> epilogue_kernel).
 //
-// Every rank owns a symmetric exchange buffer, mapped into all peers:
-//   u64 flags[(n_dim+1)][world]            arrival counter per (block, source rank)
-//   f64 data[2][world][50*n_dim + 2]       records, double-buffered on the parity of `seq`
-//   u64 poison                             set when a wait timed out (peer missing)
+// Every rank owns a symmetric exchange buffer, mapped into all peers.  Values travel in the
+// "LL" form: a double is split into two 64-bit words {low half | flag << 32}, {high half |
+// flag << 32}, written with ONE 16-byte store; `flag` encodes the exchange sequence number, so
+// THE DATA IS ITS OWN ARRIVAL FLAG -- no fence, no separate flag store, one NVLink traversal on
+// the critical path (8-byte words are single-copy atomic, so each half validates itself).
+//   u64 rec[2][world][n_dim*50 + 2][2]   records pushed by every rank, double-buffered on the
+//                                        parity of `seq` (a rank runs at most one exchange ahead)
+//   u64 var[2][n_cubes][2]               VEGAS+ only: per-cube variances, written by the owner
+//   u64 poison                           set on every rank when a wait timed out anywhere
 // Block j reduces its own partials, PUSHES its 50 (or 2) sums into slot [parity][rank] of every
-// peer's buffer with plain P2P stores, fences, releases flag[j][rank] = seq on every peer, waits
-// until flag[j][p] >= seq for all p in its own buffer, then adds the `world` slots in rank order
-// -- the same order on every rank, so all ranks refine bit-identical grids without a broadcast.
-// `seq` increases by one per call; two data buffers suffice because a rank can run at most one
-// exchange ahead of its slowest peer.
+// peer's buffer, then polls its own buffer until all `world` slots carry flag(seq) EXACTLY (a
+// stale or a later exchange never matches) and adds them in rank order -- the same order on
+// every rank, so all ranks refine bit-identical grids without a broadcast.
+// A peer that never arrives must not hang the GPU: the wait is bounded; on expiry the waiting
+// rank poisons EVERY rank's buffer, all ranks return NaN from this and every later exchange,
+// and the host raises (parallel.PeerExchange.check).
 // ---------------------------------------------------------------------------
-constexpr long long kExchangeTimeoutCycles = 20000000000ll;  // ~10 s at 2 GHz
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
 }
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+__device__ __forceinline__ void st_sys_v2(unsigned long long* p, unsigned long long a,
+                                          unsigned long long b) {
+    asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b)
+                 : "memory");
+}
+__device__ __forceinline__ void ld_sys_v2(const unsigned long long* p, unsigned long long& a,
+                                          unsigned long long& b) {
+    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p)
+                 : "memory");
+}
+__device__ __forceinline__ void st_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long* p) {
     unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 
-__global__ void __launch_bounds__(kFinThreads) exchange_epilogue_kernel(
-    double* __restrict__ workspace, int nblocks, int n_dim, int with_hist, double n_events,
-    int train, double* out_sums, double* out_hist, double* divisions, double* result, int rank,
-    int world, const __grid_constant__ PeerPtrs peers, unsigned long long seq) {
-    __shared__ double part[kFinThreads / 2][2];
-    __shared__ double row[64];
-    const bool scalars = (int)blockIdx.x == (with_hist ? n_dim : 0);
-    const int blk = scalars ? n_dim : (int)blockIdx.x;  // flag row / record section
-    const int ncols = scalars ? 2 : kBins;
-    const int col = threadIdx.x;
-    const double mine = gather_column(workspace, nblocks, scalars, blk, part);
-    const int nrec = n_dim * kBins + 2;
-    const size_t data_off = (size_t)(n_dim + 1) * world;  // u64 units, flags come first
-    const int parity = (int)(seq & 1ull);
-    const int idx = scalars ? n_dim * kBins + col : blk * kBins + col;  // packed [hist | sums]
-    if (col < ncols) {
-        for (int p = 0; p < world; ++p) {  // push to every rank (own buffer included)
-            double* slot = reinterpret_cast<double*>(peers.base[p] + data_off) +
-                           (size_t)(parity * world + rank) * nrec;
-            slot[idx] = mine;
-        }
-        __threadfence_system();
-    }
-    __syncthreads();
-    // A peer that never arrives (crashed rank, mismatched iteration counts) must not hang the
-    // GPU: the wait is bounded (~10 s); on expiry the local buffer is marked poisoned, this and
-    // every later exchange on it return NaN immediately, and the caller sees the failure.
-    unsigned long long* poison = peers.base[rank] + data_off + (size_t)2 * world * nrec;
-    if ((int)threadIdx.x < world) {
-        const int p = threadIdx.x;
-        st_release_sys(peers.base[p] + (size_t)blk * world + rank, seq);
-        const unsigned long long* flag = peers.base[rank] + (size_t)blk * world + p;
-        if (ld_acquire_sys(poison) == 0ull) {
-            const long long t_start = clock64();
-            while (ld_acquire_sys(flag) < seq) {
-                if (clock64() - t_start > kExchangeTimeoutCycles) {
-                    st_release_sys(poison, 1ull);
-                    break;
+__host__ __device__ inline size_t xchg_rec_words(int n_dim, int world) {
+    return (size_t)2 * world * (n_dim * kBins + 2) * 2;
+}
+__host__ __device__ inline size_t xchg_var_words(int64_t n_cubes) { return (size_t)4 * n_cubes; }
+
+// Exchange context of one kernel launch (kernel-parameter space).
+struct Xchg {
+    PeerPtrs peers;
+    int rank, world;
+    int n_dim;
+    long long n_cubes;             // 0 for VegasFlow / PlainFlow
+    unsigned long long seq;        // exchange sequence number, starts at 1
+    unsigned long long timeout_ns;
+};
+__device__ __forceinline__ unsigned int xchg_flag(const Xchg& x) {
+    return (unsigned int)(x.seq & 0x7fffffffull) + 1u;  // never 0 (the buffer starts zeroed)
+}
+__device__ __forceinline__ unsigned long long* xchg_poison(const Xchg& x, int p) {
+    return x.peers.base[p] + xchg_rec_words(x.n_dim, x.world) + xchg_var_words(x.n_cubes);
+}
+__device__ __forceinline__ unsigned long long* xchg_rec_slot(const Xchg& x, int p, int src,
+                                                             int idx) {
+    const int nrec = x.n_dim * kBins + 2, parity = (int)(x.seq & 1ull);
+    return x.peers.base[p] + ((size_t)(parity * x.world + src) * nrec + idx) * 2;
+}
+__device__ __forceinline__ unsigned long long* xchg_var_slot(const Xchg& x, int p, long long c) {
+    const int parity = (int)(x.seq & 1ull);
+    return x.peers.base[p] + xchg_rec_words(x.n_dim, x.world) +
+           ((size_t)parity * x.n_cubes + c) * 2;
+}
+__device__ __forceinline__ void ll_push(unsigned long long* slot, double v, unsigned int flag) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    const unsigned long long f = (unsigned long long)flag << 32;
+    st_sys_v2(slot, (b & 0xffffffffull) | f, (b >> 32) | f);
+}
+// Poll a slot of the LOCAL buffer until both halves carry `flag`.  Returns false on timeout /
+// poison (the caller then produces NaN).
+__device__ __forceinline__ bool ll_wait(const Xchg& x, const unsigned long long* slot,
+                                        unsigned int flag, double& v) {
+    unsigned long long a, b;
+    ld_sys_v2(slot, a, b);
+    if ((unsigned int)(a >> 32) != flag || (unsigned int)(b >> 32) != flag) {
+        const unsigned long long t0 = globaltimer_ns();
+        const unsigned long long* poison = xchg_poison(x, x.rank);
+        unsigned int spins = 0;
+        for (;;) {
+            ld_sys_v2(slot, a, b);
+            if ((unsigned int)(a >> 32) == flag && (unsigned int)(b >> 32) == flag) break;
+            if ((++spins & 1023u) == 0u) {
+                if (ld_sys_u64(poison) != 0ull) return false;
+                if (globaltimer_ns() - t0 > x.timeout_ns) {
+                    for (int p = 0; p < x.world; ++p) st_sys_u64(xchg_poison(x, p), 1ull);
+                    return false;
                 }
             }
         }
     }
+    v = __longlong_as_double((long long)((a & 0xffffffffull) | (b << 32)));
+    return true;
+}
+// One value per calling thread: push `mine` as record entry `idx` to every rank, wait for all
+// ranks' entry `idx`, return their sum in rank order (NaN when the exchange failed).
+__device__ __forceinline__ double xchg_allreduce_entry(const Xchg& x, int idx, double mine) {
+    const unsigned int flag = xchg_flag(x);
+    for (int p = 0; p < x.world; ++p) ll_push(xchg_rec_slot(x, p, x.rank, idx), mine, flag);
+    double tot = 0.0;
+    bool ok = ld_sys_u64(xchg_poison(x, x.rank)) == 0ull;
+    for (int p = 0; p < x.world && ok; ++p) {
+        double v;
+        ok = ll_wait(x, xchg_rec_slot(x, x.rank, p, idx), flag, v);
+        tot += v;
+    }
+    return ok ? tot : __longlong_as_double(0x7ff8000000000000ll);
+}
+
+__global__ void __launch_bounds__(kFinThreads) exchange_epilogue_kernel(
+    double* __restrict__ workspace, int nblocks, int n_dim, int with_hist, double n_events,
+    int train, double* out_sums, double* out_hist, double* divisions, double* result,
+    double* result_host, const __grid_constant__ Xchg xc) {
+    __shared__ double part[kFinThreads / 2][2];
+    __shared__ double row[64];
+    __shared__ int failed;
+    cudaTriggerProgrammaticLaunchCompletion();
+    cudaGridDependencySynchronize();
+    const bool scalars = (int)blockIdx.x == (with_hist ? n_dim : 0);
+    const int blk = scalars ? n_dim : (int)blockIdx.x;  // record section
+    const int ncols = scalars ? 2 : kBins;
+    const int col = threadIdx.x;
+    if (col == 0) failed = 0;
+    const double mine = gather_column(workspace, nblocks, scalars, blk, part);
     __syncthreads();
-    const bool poisoned = ld_acquire_sys(poison) != 0ull;
     if (col < ncols) {
-        const volatile double* data = reinterpret_cast<const volatile double*>(
-            peers.base[rank] + data_off);
-        double tot = 0.0;
-        for (int p = 0; p < world; ++p) tot += data[(size_t)(parity * world + p) * nrec + idx];
-        if (poisoned) tot = __longlong_as_double(0x7ff8000000000000ll);  // NaN
+        const int idx = scalars ? n_dim * kBins + col : blk * kBins + col;  // packed [hist | sums]
+        const double tot = xchg_allreduce_entry(xc, idx, mine);
+        if (tot != tot) failed = 1;
         if (scalars) {
             out_sums[col] = tot;
         } else {
@@ -356,31 +447,50 @@ __global__ void __launch_bounds__(kFinThreads) exchange_epilogue_kernel(
             const double res = row[0], res2 = row[1];
             const double err_tmp2 = __ddiv_rn(
                 __dsub_rn(__dmul_rn(n_events, res2), __dmul_rn(res, res)), n_events - 1.0);
+            const double sigma = sqrt(fmax(err_tmp2, 0.0));
             result[0] = res;
-            result[1] = sqrt(fmax(err_tmp2, 0.0));
+            result[1] = sigma;
+            if (result_host) {
+                result_host[0] = res;
+                result_host[1] = sigma;
+            }
         }
         return;
     }
-    if (train && !poisoned) refine_dimension(row, divisions + (size_t)blk * kEdges);
+    if (train && !failed) refine_dimension(row, divisions + (size_t)blk * kEdges);
 }
 
-size_t exchange_bytes(int n_dim, int world) {
-    // flags | double-buffered records | poison word
-    return ((size_t)(n_dim + 1) * world + (size_t)2 * world * (n_dim * kBins + 2) + 1) * 8;
+size_t exchange_bytes(int n_dim, int world, int64_t n_cubes) {
+    // LL records | LL per-cube variances (VEGAS+) | poison word
+    return (xchg_rec_words(n_dim, world) + xchg_var_words(n_cubes) + 1) * 8;
+}
+
+static Xchg make_xchg(int n_dim, int64_t n_cubes, int rank, int world, const PeerPtrs& peers,
+                      unsigned long long seq) {
+    Xchg x;
+    x.peers = peers;
+    x.rank = rank;
+    x.world = world;
+    x.n_dim = n_dim;
+    x.n_cubes = n_cubes;
+    x.seq = seq;
+    x.timeout_ns = exchange_timeout_ns();
+    return x;
 }
 
 int launch_exchange_epilogue(double* partials, int nblocks, int n_dim, bool with_hist,
                              int64_t n_events, int train, double* out_sums, double* out_hist,
-                             double* divisions, double* result, int rank, int world,
-                             const PeerPtrs& peers, unsigned long long seq, cudaStream_t stream) {
+                             double* divisions, double* result, double* result_host, int rank,
+                             int world, const PeerPtrs& peers, unsigned long long seq,
+                             cudaStream_t stream) {
     const int blocks = with_hist ? n_dim + 1 : 1;
+    const Xchg xc = make_xchg(n_dim, 0, rank, world, peers, seq);
     timing_begin(stream, 1);
-    exchange_epilogue_kernel<<<blocks, kFinThreads, 0, stream>>>(
-        partials, nblocks, n_dim, with_hist ? 1 : 0, (double)n_events, train, out_sums, out_hist,
-        divisions, result, rank, world, peers, seq);
+    VF_CUDA_CHECK(launch_pdl(exchange_epilogue_kernel, blocks, kFinThreads, 0, stream, partials,
+                             nblocks, n_dim, with_hist ? 1 : 0, (double)n_events, train, out_sums,
+                             out_hist, divisions, result, result_host, xc));
     timing_end(stream, 1);
     count_launch();
-    VF_CUDA_CHECK(cudaGetLastError());
     return VF_OK;
 }
 
@@ -559,8 +669,17 @@ int launch_accumulate(int n_dim, int64_t n, const double* w, const double* f, co
 }
 
 // ---------------------------------------------------------------------------
-// VEGAS+ epilogue (single block): arr_var (vflowplus.py:216-217), res/sigma
-// (:230-233), redistribute_samples (:153-163) and the new event offsets.
+// VEGAS+ iteration tail: arr_var (vflowplus.py:216-217), res/sigma (:230-233),
+// redistribute_samples (:153-163) and the new event offsets -- one block of 1024 threads;
+// fused with the histogram reduction + grid refinement blocks in plus_iteration_kernel.
+//
+// Multi-GPU (the reference is single-device, vflowplus.py:88-100): rank r owns
+// the contiguous cube range whose events are [~n*r/R, ~n*(r+1)/R) (boundaries on cube edges,
+// found by binary search in the event-offset prefix sum, identical on every rank).  It computes
+// the variances of ITS cubes, pushes them to every rank's buffer (all-gather of arr_var, <= 80
+// KB) together with its partial (res, sigma^2) (all-reduce), then every rank redistributes
+// redundantly from the identical gathered variances with the identical fixed-order sums -- so
+// all ranks hold bit-identical n_ev / ev_offset and never need a broadcast.
 // ---------------------------------------------------------------------------
 constexpr int kPlusThreads = 1024;
 
@@ -575,44 +694,94 @@ __device__ double block_sum_1024(double v, double* scratch) {
     return t;
 }
 
-__global__ void __launch_bounds__(kPlusThreads) plus_epilogue_kernel(
-    int64_t n_cubes, const double* __restrict__ ress, const double* __restrict__ ress2,
-    int adaptive, int min_neval, double init_calls, int32_t* n_ev, int64_t* ev_offset,
-    double* arr_var, double* result, int64_t* n_events_out) {
+struct PlusTailArgs {
+    long long n_cubes;
+    double* ress;    // [n_cubes] per-cube sum wf   (zeroed here when zero_sums)
+    double* ress2;   // [n_cubes] per-cube sum wf^2
+    int adaptive, min_neval, zero_sums;
+    double init_calls;
+    int32_t* n_ev;         // in/out
+    int64_t* ev_offset;    // in (old offsets, for the rank's cube range) / out
+    double* arr_var;       // out
+    double* result;        // [3]: res, sigma, n_events of the next iteration
+    double* result_host;   // mapped pinned copy of `result`, or null
+    int64_t* n_events_out; // or null
+};
+
+__device__ void plus_cube_block(const PlusTailArgs& a, const Xchg& xc) {
     __shared__ double scratch[kPlusThreads / 32];
     __shared__ long long scan[kPlusThreads];
+    __shared__ int failed;
+    const bool multi = xc.world > 1;
     // contiguous slice per thread so the prefix sum is a plain block scan
-    const int64_t per = (n_cubes + kPlusThreads - 1) / kPlusThreads;
-    const int64_t c0 = imin64((int64_t)threadIdx.x * per, n_cubes);
-    const int64_t c1 = imin64(c0 + per, n_cubes);
-    double res = 0.0, sig2 = 0.0, damp = 0.0;
-    for (int64_t c = c0; c < c1; ++c) {
-        const double fn = (double)n_ev[c];
-        const double r1 = ress[c];
-        const double var = __dsub_rn(__dmul_rn(ress2[c], fn), __dmul_rn(r1, r1));  // :216-217
-        arr_var[c] = var;
-        res += r1;                                   // :231
-        const double v0 = fmax(var, 0.0);            // :230
-        sig2 += __ddiv_rn(v0, fn - 1.0);             // :232
-        if (adaptive) damp += pow(v0, kBeta / 2);    // :157 (clamped, documented divergence)
+    const int64_t per = (a.n_cubes + kPlusThreads - 1) / kPlusThreads;
+    const int64_t c0 = imin64((int64_t)threadIdx.x * per, a.n_cubes);
+    const int64_t c1 = imin64(c0 + per, a.n_cubes);
+    if (threadIdx.x == 0) failed = 0;
+    __syncthreads();
+    double res = 0.0, sig2 = 0.0;
+    if (!multi) {
+        for (int64_t c = c0; c < c1; ++c) {
+            const double fn = (double)a.n_ev[c];
+            const double r1 = a.ress[c];
+            const double var = __dsub_rn(__dmul_rn(a.ress2[c], fn), __dmul_rn(r1, r1));  // :216-217
+            a.arr_var[c] = var;
+            res += r1;                                        // :231
+            sig2 += __ddiv_rn(fmax(var, 0.0), fn - 1.0);      // :230, :232
+        }
+        res = block_sum_1024(res, scratch);
+        sig2 = block_sum_1024(sig2, scratch);
+    } else {
+        const unsigned int flag = xchg_flag(xc);
+        const int64_t n = a.ev_offset[a.n_cubes];
+        const int64_t lo = first_cube_at_or_after(a.ev_offset, a.n_cubes, n * xc.rank / xc.world);
+        const int64_t hi =
+            first_cube_at_or_after(a.ev_offset, a.n_cubes, n * (xc.rank + 1) / xc.world);
+        for (int64_t c = lo + threadIdx.x; c < hi; c += kPlusThreads) {
+            const double fn = (double)a.n_ev[c];
+            const double r1 = a.ress[c];
+            const double var = __dsub_rn(__dmul_rn(a.ress2[c], fn), __dmul_rn(r1, r1));
+            for (int p = 0; p < xc.world; ++p) ll_push(xchg_var_slot(xc, p, c), var, flag);
+            res += r1;
+            sig2 += __ddiv_rn(fmax(var, 0.0), fn - 1.0);
+        }
+        res = block_sum_1024(res, scratch);
+        sig2 = block_sum_1024(sig2, scratch);
+        __shared__ double tot[2];
+        if (threadIdx.x < 2)
+            tot[threadIdx.x] = xchg_allreduce_entry(xc, xc.n_dim * kBins + threadIdx.x,
+                                                    threadIdx.x == 0 ? res : sig2);
+        // gather every cube's variance from the local buffer (each arrives flagged)
+        bool ok = ld_sys_u64(xchg_poison(xc, xc.rank)) == 0ull;
+        for (int64_t c = c0; c < c1 && ok; ++c) {
+            double v;
+            ok = ll_wait(xc, xchg_var_slot(xc, xc.rank, c), flag, v);
+            a.arr_var[c] = v;
+        }
+        if (!ok) failed = 1;
+        __syncthreads();
+        res = tot[0];
+        sig2 = tot[1];
+        if (failed) res = sig2 = __longlong_as_double(0x7ff8000000000000ll);
     }
-    res = block_sum_1024(res, scratch);
-    sig2 = block_sum_1024(sig2, scratch);
-    if (threadIdx.x == 0) {
-        result[0] = res;
-        result[1] = sqrt(sig2);  // :233
-    }
-    if (!adaptive) return;
-    const double dsum = block_sum_1024(damp, scratch);
+    if (a.zero_sums)
+        for (int64_t c = c0; c < c1; ++c) a.ress[c] = a.ress2[c] = 0.0;
+    const bool redistribute = a.adaptive && !failed;
+    double damp = 0.0;
+    if (redistribute)
+        for (int64_t c = c0; c < c1; ++c)
+            damp += pow(fmax(a.arr_var[c], 0.0), kBeta / 2);  // :157 (clamped, documented)
+    const double dsum = redistribute ? block_sum_1024(damp, scratch) : 0.0;
     long long local = 0;
     for (int64_t c = c0; c < c1; ++c) {
-        int32_t nv = n_ev[c];
-        if (dsum > 0.0) {
-            const double d = pow(fmax(arr_var[c], 0.0), kBeta / 2);
-            const double want = __ddiv_rn(__ddiv_rn(__dmul_rn(d, init_calls), 2.0), dsum);  // :160
-            nv = (int32_t)fmax((double)min_neval, want);                                    // :158-162
+        int32_t nv = a.n_ev[c];
+        if (redistribute && dsum > 0.0) {
+            const double d = pow(fmax(a.arr_var[c], 0.0), kBeta / 2);
+            const double want =
+                __ddiv_rn(__ddiv_rn(__dmul_rn(d, a.init_calls), 2.0), dsum);  // :160
+            nv = (int32_t)fmax((double)a.min_neval, want);                    // :158-162
+            a.n_ev[c] = nv;
         }
-        n_ev[c] = nv;
         local += nv;
     }
     scan[threadIdx.x] = local;
@@ -623,26 +792,123 @@ __global__ void __launch_bounds__(kPlusThreads) plus_epilogue_kernel(
         scan[threadIdx.x] += v;
         __syncthreads();
     }
-    long long run = scan[threadIdx.x] - local;  // exclusive prefix of this slice
-    for (int64_t c = c0; c < c1; ++c) {
-        ev_offset[c] = run;
-        run += n_ev[c];
+    const long long total = scan[kPlusThreads - 1];
+    if (a.adaptive && a.ev_offset) {
+        long long run = scan[threadIdx.x] - local;  // exclusive prefix of this slice
+        for (int64_t c = c0; c < c1; ++c) {
+            a.ev_offset[c] = run;
+            run += a.n_ev[c];
+        }
+        if (threadIdx.x == kPlusThreads - 1) a.ev_offset[a.n_cubes] = total;
     }
-    if (threadIdx.x == kPlusThreads - 1) {
-        ev_offset[n_cubes] = scan[kPlusThreads - 1];
-        *n_events_out = scan[kPlusThreads - 1];  // :163
+    if (threadIdx.x == 0) {
+        const double sigma = sqrt(sig2);  // :233
+        a.result[0] = res;
+        a.result[1] = sigma;
+        a.result[2] = (double)total;  // :163
+        if (a.result_host) {
+            a.result_host[0] = res;
+            a.result_host[1] = sigma;
+            a.result_host[2] = (double)total;
+        }
+        if (a.n_events_out) *a.n_events_out = total;
     }
+}
+
+// Stand-alone form (vfp_iteration_epilogue): `result` has room for two doubles only.
+__global__ void __launch_bounds__(kPlusThreads) plus_epilogue_kernel(
+    const __grid_constant__ PlusTailArgs a, const __grid_constant__ Xchg xc, double* result2) {
+    __shared__ double res3[3];
+    PlusTailArgs b = a;
+    b.result = res3;
+    plus_cube_block(b, xc);
+    if (threadIdx.x == 0) {
+        result2[0] = res3[0];
+        result2[1] = res3[1];
+    }
+}
+
+// Whole tail of a VEGAS+ iteration in one launch: blocks [0, n_dim) reduce (and, multi-GPU,
+// exchange) one histogram row each and refine that dimension (only when training), the last
+// block is plus_cube_block.
+__global__ void __launch_bounds__(kPlusThreads) plus_iteration_kernel(
+    double* __restrict__ workspace, int nblocks, int n_dim, int train, double* out_hist,
+    double* divisions, const __grid_constant__ PlusTailArgs a, const __grid_constant__ Xchg xc) {
+    __shared__ double row[64];
+    __shared__ int failed;
+    pdl_launch_dependents();
+    pdl_wait();
+    const int cube_block = train ? n_dim : 0;
+    if ((int)blockIdx.x == cube_block) {
+        plus_cube_block(a, xc);
+        return;
+    }
+    const int blk = blockIdx.x, col = threadIdx.x;
+    if (col == 0) failed = 0;
+    __syncthreads();
+    if (col < kBins) {
+        double tot = gather_column(workspace, nblocks, false, blk, nullptr);
+        if (xc.world > 1) {
+            tot = xchg_allreduce_entry(xc, blk * kBins + col, tot);
+            if (tot != tot) failed = 1;
+        }
+        out_hist[(size_t)blk * kBins + col] = tot;
+        row[col] = tot;
+    }
+    __syncthreads();
+    if (!failed) refine_dimension(row, divisions + (size_t)blk * kEdges);
+}
+
+static PlusTailArgs make_tail(int64_t n_cubes, double* ress, double* ress2, int adaptive,
+                              int min_neval, int64_t init_calls, int32_t* n_ev, int64_t* ev_offset,
+                              double* arr_var, double* result, double* result_host,
+                              int64_t* n_events_out, int zero_sums) {
+    PlusTailArgs a;
+    a.n_cubes = n_cubes;
+    a.ress = ress;
+    a.ress2 = ress2;
+    a.adaptive = adaptive;
+    a.min_neval = min_neval;
+    a.zero_sums = zero_sums;
+    a.init_calls = (double)init_calls;
+    a.n_ev = n_ev;
+    a.ev_offset = ev_offset;
+    a.arr_var = arr_var;
+    a.result = result;
+    a.result_host = result_host;
+    a.n_events_out = n_events_out;
+    return a;
 }
 
 int launch_plus_epilogue(int64_t n_cubes, const double* ress, const double* ress2, int adaptive,
                          int min_neval, int64_t init_calls, int32_t* n_ev, int64_t* ev_offset,
                          double* arr_var, double* result, int64_t* n_events_out,
                          cudaStream_t stream) {
-    plus_epilogue_kernel<<<1, kPlusThreads, 0, stream>>>(n_cubes, ress, ress2, adaptive, min_neval,
-                                                         (double)init_calls, n_ev, ev_offset,
-                                                         arr_var, result, n_events_out);
+    const PlusTailArgs a =
+        make_tail(n_cubes, const_cast<double*>(ress), const_cast<double*>(ress2), adaptive,
+                  min_neval, init_calls, n_ev, ev_offset, arr_var, nullptr, nullptr, n_events_out, 0);
+    PeerPtrs none = {};
+    const Xchg xc = make_xchg(1, 0, 0, 1, none, 1);
+    plus_epilogue_kernel<<<1, kPlusThreads, 0, stream>>>(a, xc, result);
     count_launch();
     VF_CUDA_CHECK(cudaGetLastError());
+    return VF_OK;
+}
+
+int launch_plus_iteration_tail(double* workspace, int nblocks, int n_dim, int train,
+                               double* out_hist, double* divisions, int64_t n_cubes, double* ress,
+                               double* ress2, int adaptive, int min_neval, int64_t init_calls,
+                               int32_t* n_ev, int64_t* ev_offset, double* arr_var, double* result,
+                               double* result_host, int rank, int world, const PeerPtrs& peers,
+                               unsigned long long seq, cudaStream_t stream) {
+    const PlusTailArgs a = make_tail(n_cubes, ress, ress2, adaptive, min_neval, init_calls, n_ev,
+                                     ev_offset, arr_var, result, result_host, nullptr, 1);
+    const Xchg xc = make_xchg(n_dim, world > 1 ? n_cubes : 0, rank, world, peers, seq);
+    timing_begin(stream, 1);
+    VF_CUDA_CHECK(launch_pdl(plus_iteration_kernel, train ? n_dim + 1 : 1, kPlusThreads, 0, stream,
+                             workspace, nblocks, n_dim, train, out_hist, divisions, a, xc));
+    timing_end(stream, 1);
+    count_launch();
     return VF_OK;
 }
 

@@ -13,12 +13,20 @@ int launch_finalize(double* partials, int nblocks, int n_dim, bool with_hist,
                     double* out_sums, double* out_hist, int accumulate, cudaStream_t stream);
 int launch_finalize_epilogue(double* partials, int nblocks, int n_dim, bool with_hist,
                              int64_t n_events, int train, double* out_sums, double* out_hist,
-                             double* divisions, double* result, cudaStream_t stream);
-size_t exchange_bytes(int n_dim, int world);
+                             double* divisions, double* result, double* result_host,
+                             cudaStream_t stream);
+size_t exchange_bytes(int n_dim, int world, int64_t n_cubes);
 int launch_exchange_epilogue(double* partials, int nblocks, int n_dim, bool with_hist,
                              int64_t n_events, int train, double* out_sums, double* out_hist,
-                             double* divisions, double* result, int rank, int world,
-                             const PeerPtrs& peers, unsigned long long seq, cudaStream_t stream);
+                             double* divisions, double* result, double* result_host, int rank,
+                             int world, const PeerPtrs& peers, unsigned long long seq,
+                             cudaStream_t stream);
+int launch_plus_iteration_tail(double* workspace, int nblocks, int n_dim, int train,
+                               double* out_hist, double* divisions, int64_t n_cubes, double* ress,
+                               double* ress2, int adaptive, int min_neval, int64_t init_calls,
+                               int32_t* n_ev, int64_t* ev_offset, double* arr_var, double* result,
+                               double* result_host, int rank, int world, const PeerPtrs& peers,
+                               unsigned long long seq, cudaStream_t stream);
 int launch_refine(int n_dim, const double* hist, double* divisions, cudaStream_t stream);
 int launch_epilogue(int n_dim, int64_t n_events, int train, const double* sums, const double* hist,
                     double* divisions, double* result, cudaStream_t stream);

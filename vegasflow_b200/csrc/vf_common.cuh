@@ -6,6 +6,8 @@
 #endif
 #include <stdint.h>
 
+#include <utility>
+
 #include "../../include/vegasflow_b200.h"
 
 namespace vf {
@@ -27,6 +29,36 @@ int sm_count();
 // optional CUDA-event bracket around the event kernels (vf_kernel_timing)
 void timing_begin(cudaStream_t stream, int category = 0);
 void timing_end(cudaStream_t stream, int category = 0);
+
+// ---- programmatic dependent launch (sm_90+) ------------------------------------------------
+// Every kernel of the iteration chain (event kernel -> reduce/exchange/refine kernel -> next
+// event kernel) is launched with cudaLaunchAttributeProgrammaticStreamSerialization: a kernel
+// releases its successor at its very start (the successor's blocks become resident as SM
+// resources free up, hiding the launch latency) and waits for the COMPLETION of its predecessor
+// (griddepcontrol.wait) before touching anything the predecessor writes.  Without the launch
+// attribute both instructions are no-ops.
+#ifndef VF_HOST_SHIM
+__device__ __forceinline__ void pdl_launch_dependents() {
+    asm volatile("griddepcontrol.launch_dependents;");
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), int grid, int block, size_t smem,
+                              cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
+#endif
 
 #define VF_CUDA_CHECK(expr)                                   \
     do {                                                      \
@@ -155,6 +187,18 @@ __device__ __forceinline__ double div_rn_by(double y, double b, double rb) {
     const double q0 = __dmul_rn(y, rb);
     const double r = __fma_rn(-b, q0, y);
     return __fma_rn(r, rb, q0);
+}
+
+// VEGAS+ multi-GPU partition: smallest cube c in [0, n_cubes] with ev_offset[c] >= target.
+// Rank r of R owns cubes [f(n*r/R), f(n*(r+1)/R)), a pure function of the offsets.
+__device__ __forceinline__ int64_t first_cube_at_or_after(const int64_t* __restrict__ ev_offset,
+                                                          int64_t n_cubes, int64_t target) {
+    int64_t lo = 0, hi = n_cubes;  // answer in [lo, hi]
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (ev_offset[mid] >= target) hi = mid; else lo = mid + 1;
+    }
+    return lo;
 }
 
 __device__ __forceinline__ double warp_sum(double v) {

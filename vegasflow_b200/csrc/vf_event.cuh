@@ -36,7 +36,8 @@ constexpr int min_blocks() {
 }
 
 // The stratified kernel carries the cube state (coordinates, counts, per-cube sums) on top of
-// the event state; for d > 4 it needs the 128-register budget to stay spill-free.
+// the event state.  Two resident blocks per SM (64-register budget, a few spilled words at
+// d = 8) measured faster than one spill-free block with 128 registers.
 template <class I, int NDIM>
 constexpr int plus_min_blocks() {
     return (NDIM <= 8 && !I::kHeavy) ? 2 : 1;
@@ -54,11 +55,15 @@ struct EventKernelArgs {
     IntegrandConsts ic;
 };
 
-// Stage (x_ini, Delta) pairs and zero the histogram copies.
+// Zero the histogram copies (independent of the previous kernel), wait for the previous kernel
+// of the stream (it refines `divisions`), then stage the (x_ini, Delta) pairs.
 template <int NDIM>
 __device__ __forceinline__ void stage_grid(const double* __restrict__ divisions, double2* tbl,
                                            double* hist, bool zero_hist) {
     using C = Cfg<NDIM>;
+    if (zero_hist)
+        for (int i = threadIdx.x; i < C::kHistEntries; i += blockDim.x) hist[i] = 0.0;
+    pdl_wait();
     for (int i = threadIdx.x; i < C::kTblEntries; i += blockDim.x) {
         const int jb = i / C::TC;
         const int j = jb / kBins, b = jb - j * kBins;
@@ -66,8 +71,6 @@ __device__ __forceinline__ void stage_grid(const double* __restrict__ divisions,
         const double x_fin = divisions[j * kEdges + b + 1];  // vflow.py:71
         tbl[i] = make_double2(x_ini, __dsub_rn(x_fin, x_ini));  // vflow.py:73
     }
-    if (zero_hist)
-        for (int i = threadIdx.x; i < C::kHistEntries; i += blockDim.x) hist[i] = 0.0;
 }
 
 // monte_carlo.py:270-274: w *= xjac; x = xmin + x*xdelta; w *= prod(xdelta)
@@ -159,9 +162,12 @@ event_kernel(const __grid_constant__ EventKernelArgs a) {
     double2* tbl = reinterpret_cast<double2*>(smem_raw);
     double* hist = reinterpret_cast<double*>(smem_raw + (size_t)C::kTblEntries * 16);
     const bool do_hist = (MODE == VF_MODE_VEGAS) && a.train;
+    pdl_launch_dependents();  // the reduce/refine kernel may get resident behind this grid
     if (MODE == VF_MODE_VEGAS) {
         stage_grid<NDIM>(a.divisions, tbl, hist, do_hist);
         __syncthreads();
+    } else {
+        pdl_wait();  // the previous tail kernel still reads the per-block records
     }
     const int lane = threadIdx.x & 31;
     const char* tbl_lane = reinterpret_cast<const char*>(tbl) + (lane % C::TC) * 16;
@@ -283,8 +289,10 @@ struct PlusKernelArgs {
     double* w;
     int32_t* ind;
     double* wf;
-    int64_t n_cubes, n_events;
+    int64_t n_cubes;
+    int64_t n_events;  // < 0: read ev_offset[n_cubes] on the device (no host copy of the count)
     int n_strat;
+    int rank, world;   // multi-GPU: this rank evaluates the events of its cube range
     double xjac;
     uint32_t iteration;
     int train;
@@ -301,14 +309,25 @@ plus_event_kernel(const __grid_constant__ PlusKernelArgs a) {
     double2* tbl = reinterpret_cast<double2*>(smem_raw);
     double* hist = reinterpret_cast<double*>(smem_raw + (size_t)C::kTblEntries * 16);
     const bool do_hist = a.train != 0;
-    stage_grid<NDIM>(a.divisions, tbl, hist, do_hist);
+    pdl_launch_dependents();
+    stage_grid<NDIM>(a.divisions, tbl, hist, do_hist);  // waits for the previous tail kernel
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const char* tbl_lane = reinterpret_cast<const char*>(tbl) + (lane % C::TC) * 16;
     char* hist_lane = reinterpret_cast<char*>(hist) + (lane % C::HC) * 8;
-    const int64_t per_block = (a.n_events + gridDim.x - 1) / gridDim.x;
-    const int64_t begin = (int64_t)blockIdx.x * per_block;
-    const int64_t end = min(begin + per_block, a.n_events);
+    // the sample allocation lives on the device: after redistribute_samples the event count of
+    // the next iteration is ev_offset[n_cubes] (vflowplus.py:163), never copied to the host
+    const int64_t n_events = a.n_events >= 0 ? a.n_events : a.ev_offset[a.n_cubes];
+    int64_t ev_lo = 0, ev_hi = n_events;
+    if (a.world > 1) {  // contiguous cube range balanced on the event prefix sum
+        ev_lo = a.ev_offset[first_cube_at_or_after(a.ev_offset, a.n_cubes,
+                                                   n_events * a.rank / a.world)];
+        ev_hi = a.ev_offset[first_cube_at_or_after(a.ev_offset, a.n_cubes,
+                                                   n_events * (a.rank + 1) / a.world)];
+    }
+    const int64_t per_block = (ev_hi - ev_lo + gridDim.x - 1) / gridDim.x;
+    const int64_t begin = ev_lo + (int64_t)blockIdx.x * per_block;
+    const int64_t end = min(begin + per_block, ev_hi);
     const double fstrat = (double)a.n_strat;
     const double rstrat = __ddiv_rn(1.0, fstrat);
 
@@ -459,11 +478,10 @@ int launch_event_dim(const EventLaunch& L) {
     const int64_t n = (int64_t)(L.k.ev_end - L.k.ev_begin);
     const int blocks = grid_blocks_for(n, C::kThreads, min_blocks<I, NDIM>());
     timing_begin(L.stream);
-    kern<<<blocks, C::kThreads, smem, L.stream>>>(L.k);
+    VF_CUDA_CHECK(launch_pdl(kern, blocks, C::kThreads, smem, L.stream, L.k));
     timing_end(L.stream);
     count_launch();
     *L.nblocks_out = blocks;
-    VF_CUDA_CHECK(cudaGetLastError());
     return VF_OK;
 }
 
@@ -493,15 +511,23 @@ int launch_plus_dim(const PlusLaunch& L) {
     auto kern = ext ? plus_event_kernel<I, NDIM, true, 52>
                     : (L.rng_bits == 32 ? plus_event_kernel<I, NDIM, false, 32>
                                         : plus_event_kernel<I, NDIM, false, 52>);
-    VF_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)C::kSmemBytes));
-    const int blocks = grid_blocks_for(L.k.n_events, C::kThreads, plus_min_blocks<I, NDIM>());
+    // opt in to > 48 KB dynamic shared memory once per (variant, device)
+    static std::atomic<uint64_t> configured[3];
+    const int variant = ext ? 0 : (L.rng_bits == 32 ? 1 : 2), dev = current_device();
+    if (!(configured[variant].load(std::memory_order_acquire) >> dev & 1ull)) {
+        VF_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)C::kSmemBytes));
+        configured[variant].fetch_or(1ull << dev, std::memory_order_release);
+    }
+    // device-resident event count (n_events < 0): always the full grid, idle blocks exit at once
+    const int blocks = L.k.n_events >= 0
+                           ? grid_blocks_for(L.k.n_events, C::kThreads, plus_min_blocks<I, NDIM>())
+                           : sm_count() * plus_min_blocks<I, NDIM>();
     timing_begin(L.stream);
-    kern<<<blocks, C::kThreads, C::kSmemBytes, L.stream>>>(L.k);
+    VF_CUDA_CHECK(launch_pdl(kern, blocks, C::kThreads, C::kSmemBytes, L.stream, L.k));
     timing_end(L.stream);
     count_launch();
     *L.nblocks_out = blocks;
-    VF_CUDA_CHECK(cudaGetLastError());
     return VF_OK;
 }
 

@@ -11,12 +11,16 @@ Reference bodies (file:line relative to /root/reference):
   drellyan_lo   examples/drellyan_lo_tf.py:27-249   (n_dim = 4)
   singletop_lo  examples/singletop_lo_tf.py:45-270  (n_dim = 3)
 """
+import fcntl
 import hashlib
 import math
 import os
 import subprocess
 
 import torch
+
+# largest n_dim whose fused-kernel shared memory (n_dim * 9600 B) fits the 227 KB opt-in limit
+MAX_FUSED_DIM = 24
 
 
 class BuiltinIntegrand:
@@ -89,8 +93,10 @@ def cuda_integrand(source, n_dim, name="user_integrand", heavy=False, verbose=Fa
     from vegasflow_b200 import build as vf_build
 
     n_dim = int(n_dim)
-    if not 1 <= n_dim <= 32:
-        raise ValueError("cuda_integrand supports 1 <= n_dim <= 32")
+    # the fused kernels keep n_dim*9600 B of tables + histograms in shared memory: 24 dimensions
+    # fill the 227 KB a block can opt in to on sm_100
+    if not 1 <= n_dim <= MAX_FUSED_DIM:
+        raise ValueError(f"cuda_integrand supports 1 <= n_dim <= {MAX_FUSED_DIM}")
     vf_build.build()
     with open(os.path.join(vf_build.CSRC, "vf_user_integrand.cu.in")) as fh:
         template = fh.read()
@@ -104,19 +110,35 @@ def cuda_integrand(source, n_dim, name="user_integrand", heavy=False, verbose=Fa
     cu_path = os.path.join(out_dir, f"{name}_{digest}.cu")
     so_path = os.path.join(out_dir, f"{name}_{digest}.so")
     if not os.path.exists(so_path):
-        with open(cu_path, "w") as fh:
-            fh.write(unit)
-        flags = [f for f in vf_build.NVCC_FLAGS if f not in ("-Xptxas", "-v")]
-        cmd = [vf_build._nvcc(), *flags, "-shared", "-I", vf_build.INCLUDE, "-I", vf_build.CSRC,
-               cu_path, "-o", so_path + ".tmp", "-L", vf_build.LIBDIR, "-lvegasflow_b200",
-               "-Xlinker", "-rpath", "-Xlinker", vf_build.LIBDIR]
-        res = subprocess.run(cmd, capture_output=True, text=True)
-        if res.returncode != 0:
-            raise ValueError(f"nvcc failed on the user integrand:\n{res.stdout}\n{res.stderr}")
-        if verbose:
-            print(res.stderr)
-        os.replace(so_path + ".tmp", so_path)
+        # one builder per module at a time (torchrun: every rank sees the empty cache at once)
+        with open(os.path.join(out_dir, f".{name}_{digest}.lock"), "w") as lock:
+            fcntl.flock(lock, fcntl.LOCK_EX)
+            try:
+                if not os.path.exists(so_path):  # another rank built it while we waited
+                    _compile_user_module(vf_build, unit, cu_path, so_path, verbose)
+            finally:
+                fcntl.flock(lock, fcntl.LOCK_UN)
     return CudaIntegrand(name, n_dim, so_path)
+
+
+def _compile_user_module(vf_build, unit, cu_path, so_path, verbose):
+    tmp_cu = f"{cu_path}.{os.getpid()}.tmp.cu"
+    tmp_so = f"{so_path}.{os.getpid()}.tmp"
+    with open(tmp_cu, "w") as fh:
+        fh.write(unit)
+    os.replace(tmp_cu, cu_path)
+    flags = [f for f in vf_build.NVCC_FLAGS if f not in ("-Xptxas", "-v")]
+    cmd = [vf_build._nvcc(), *flags, "-shared", "-I", vf_build.INCLUDE, "-I", vf_build.CSRC,
+           cu_path, "-o", tmp_so, "-L", vf_build.LIBDIR, "-lvegasflow_b200",
+           "-Xlinker", "-rpath", "-Xlinker", vf_build.LIBDIR]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        if os.path.exists(tmp_so):
+            os.remove(tmp_so)
+        raise ValueError(f"nvcc failed on the user integrand:\n{res.stdout}\n{res.stderr}")
+    if verbose:
+        print(res.stderr)
+    os.replace(tmp_so, so_path)  # atomic: a concurrent loader never sees a half-written module
 
 
 def _symgauss_torch(xarr):

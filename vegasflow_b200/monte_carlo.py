@@ -69,6 +69,7 @@ class MonteCarloFlow(ABC):
     """
 
     _CAN_RUN_VECTORIAL = False
+    _ROW = 2  # doubles per result row: (res, sigma)
     _MODE = _lib.MODE_PLAIN
     # True when whole iterations can be enqueued by vf_run_iterations (single rank, fused)
     _BATCHABLE = False
@@ -157,19 +158,41 @@ class MonteCarloFlow(ABC):
         self._workspace = torch.zeros(nbytes // 8, dtype=DTYPE, device=self._device)
         # packed per-iteration buffer: histogram [n_dim*50] then (sum wf, sum wf^2)
         self._packed = torch.zeros(self.n_dim * BINS_MAX + 2, dtype=DTYPE, device=self._device)
-        self._results = torch.zeros((64, 2), dtype=DTYPE, device=self._device)
+        self._results = torch.zeros((64, self._ROW), dtype=DTYPE, device=self._device)
         self._results_used = 0
+        # page-locked, device-mapped mirror of the rows of the LAST batched call: the tail
+        # kernel of every iteration stores its row there, the host reads it after ONE stream
+        # synchronisation (no blocking device->host copy per iteration)
+        self._host_rows = torch.zeros((64, self._ROW), dtype=DTYPE).pin_memory()
+        self._host_rows_n = 0
 
     def _result_rows(self, n):
-        """`n` consecutive device rows that receive (res, sigma) of the next iterations."""
+        """`n` consecutive device rows that receive (res, sigma[, ...]) of the next iterations."""
         if self._results_used + n > self._results.shape[0]:
             size = max(2 * self._results.shape[0], self._results_used + n)
-            grown = torch.zeros((size, 2), dtype=DTYPE, device=self._device)
+            grown = torch.zeros((size, self._ROW), dtype=DTYPE, device=self._device)
             grown[: self._results.shape[0]] = self._results
             self._results = grown
         rows = self._results[self._results_used : self._results_used + n]
         self._results_used += n
         self._last_row = rows[n - 1]
+        return rows
+
+    def _host_ring(self, n):
+        """Pinned host rows for the next `n` iterations of a batched call."""
+        if n > self._host_rows.shape[0]:
+            torch.cuda.current_stream().synchronize()  # nothing in flight may write the old one
+            self._host_rows = torch.zeros((max(n, 2 * self._host_rows.shape[0]), self._ROW),
+                                          dtype=DTYPE).pin_memory()
+        self._host_rows_n = n
+        return self._host_rows
+
+    def _fetch_rows(self):
+        """Host copies [(res, sigma[, ...])] of the last batched call: one stream sync."""
+        torch.cuda.current_stream().synchronize()
+        rows = self._host_rows[: self._host_rows_n].tolist()
+        if any(r[0] != r[0] for r in rows) and self._exchange is not None:
+            self._exchange.check()
         return rows
 
     def _result_slot(self):
@@ -198,6 +221,7 @@ class MonteCarloFlow(ABC):
         lib = _lib.load()
         begin, end = parallel.shard_range(self.n_events)
         rows = self._result_rows(n_iter)
+        host = self._host_ring(n_iter)
         first_seq = xchg.seq + 1
         xchg.seq += n_iter
         _lib.check(
@@ -206,7 +230,7 @@ class MonteCarloFlow(ABC):
                 self.n_events, self._seed, self._iteration, n_iter,
                 int(bool(getattr(self, "train", False))), _lib.ptr(self._grid_tensor()),
                 self._xmin_c, self._xdelta_c, _lib.ptr(self._packed), _lib.ptr(rows),
-                _lib.ptr(self._workspace), self._workspace.numel() * 8, xchg.rank,
+                _lib.ptr(host), _lib.ptr(self._workspace), self._workspace.numel() * 8, xchg.rank,
                 xchg.world_size, xchg.ptrs, first_seq, _lib.stream_ptr(),
             )
         )
@@ -230,12 +254,13 @@ class MonteCarloFlow(ABC):
         self._ensure_device()
         lib = _lib.load()
         rows = self._result_rows(n_iter)
+        host = self._host_ring(n_iter)
         _lib.check(
             lib.vf_run_iterations(
                 self._mode_word, self._builtin.integrand_id(), self.n_dim, self.n_events, self._seed,
                 self._iteration, n_iter, int(bool(getattr(self, "train", False))),
                 _lib.ptr(self._grid_tensor()), self._xmin_c, self._xdelta_c,
-                _lib.ptr(self._packed), _lib.ptr(rows), _lib.ptr(self._workspace),
+                _lib.ptr(self._packed), _lib.ptr(rows), _lib.ptr(host), _lib.ptr(self._workspace),
                 self._workspace.numel() * 8, _lib.stream_ptr(),
             )
         )
@@ -393,7 +418,11 @@ class MonteCarloFlow(ABC):
         return out
 
     def _allreduce(self, out):
-        parallel.allreduce_sum_(self._packed)
+        """NCCL path: all-reduce what this iteration produced -- the whole packed buffer when a
+        histogram was filled, only the two sums otherwise (frozen grid, PlainFlow: the histogram
+        section is stale there and must not be multiplied by the world size every iteration)."""
+        with_hist = self._MODE == _lib.MODE_VEGAS and bool(getattr(self, "train", False))
+        parallel.allreduce_sum_(self._packed if with_hist else self._sums)
 
     # ------------------------------------------------------------------ compile
     def compile(self, integrand, compilable=True, signature=None, trace=False, check=True):
@@ -518,9 +547,13 @@ class MonteCarloFlow(ABC):
             for k in range(n_iter):
                 all_results.append((rows[k, 0], rows[k, 1]))
                 self._history.append((rows[k, 0], rows[k, 1], None))
+            host_rows = self._fetch_rows()
+            self._after_batch(host_rows)
+            self._host_rows_n = 0
         for i in range(0 if batched else n_iter):
             start = time.time() if log_time else None
             self._last_row = None
+            self._host_rows_n = 0
             res, error = self._run_iteration()
             all_results.append((res, error))
             # monte_carlo.py:688-694: store the user histograms of this iteration and empty them
@@ -531,8 +564,8 @@ class MonteCarloFlow(ABC):
                 for h in histograms:
                     h.zero_()
             if self._verbose:
-                if self._last_row is not None:  # one 16-byte device->host read
-                    res_h, err_h = self._last_row.tolist()
+                if self._last_row is not None:  # the row already sits in pinned host memory
+                    res_h, err_h = self._row_to_host()
                     res, error = res_h, err_h
                     all_results[-1] = (res, error)
                 else:
@@ -550,7 +583,7 @@ class MonteCarloFlow(ABC):
 
         # One read-back for everything that is still on the device
         if batched:
-            host = [tuple(row) for row in rows.detach().cpu().tolist()]
+            host = [(row[0], row[1]) for row in host_rows]
         else:
             host = [(self._to_host(r), self._to_host(e)) for r, e in all_results]
         for k, (r, e) in enumerate(host):
@@ -592,13 +625,27 @@ class MonteCarloFlow(ABC):
             raise RuntimeError("Compile must be ran before running any iterations")
         self._ensure_device()
         self._last_row = None
+        self._host_rows_n = 0
         res, error = self._run_iteration()
         if self._last_row is not None:
-            res, error = self._last_row.tolist()
+            res, error = self._row_to_host()
         else:
             res, error = self._to_host(res), self._to_host(error)
         self._history.append((res, error, None))
         return res, error
+
+    def _row_to_host(self):
+        """(res, sigma) of the iteration just enqueued, on the host."""
+        if self._host_rows_n:  # batched call: the tail kernel wrote the row to pinned memory
+            rows = self._fetch_rows()
+            self._after_batch(rows)
+            self._host_rows_n = 0
+            return rows[-1][0], rows[-1][1]
+        res, error = self._last_row[:2].tolist()
+        return res, error
+
+    def _after_batch(self, host_rows):
+        """Hook: host-side bookkeeping from the rows of a batched call (VEGAS+ event count)."""
 
     @staticmethod
     def _to_host(v):

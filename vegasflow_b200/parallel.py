@@ -46,11 +46,13 @@ class PeerExchange:
     refine kernel (`vf_run_iteration_sharded`).  One per integrator instance.
 
     The buffer is allocated with torch symmetric memory so every rank holds device pointers to
-    all peers' copies; the kernel pushes its [n_dim*50+2] sums into every peer with P2P stores
-    and synchronises with release/acquire flags -- no NCCL call on the iteration path.
+    all peers' copies; the kernel pushes its [n_dim*50+2] sums (VEGAS+: also the per-cube
+    variances of its cube range) into every peer with 16-byte P2P stores that carry the value AND
+    the exchange sequence number, so arrival is detected on the data itself -- no fence, no
+    separate flag, no NCCL call on the iteration path.
     """
 
-    def __init__(self, n_dim, device):
+    def __init__(self, n_dim, device, n_cubes=0):
         import torch.distributed._symmetric_memory as symm_mem
 
         from vegasflow_b200 import _lib
@@ -58,7 +60,7 @@ class PeerExchange:
         rank, world_size = world()
         if world_size > 8:
             raise RuntimeError("the peer exchange covers the GPUs of one NVLink box (<= 8)")
-        nbytes = _lib.load().vf_exchange_bytes(int(n_dim), world_size)
+        nbytes = _lib.load().vf_exchange_bytes(int(n_dim), world_size, int(n_cubes))
         self.buf = symm_mem.empty(nbytes // 8, dtype=torch.int64, device=device)
         self.hdl = symm_mem.rendezvous(self.buf, dist.group.WORLD)
         self.buf.zero_()
@@ -75,14 +77,23 @@ class PeerExchange:
         self.seq += 1
         return self.seq
 
+    def check(self):
+        """Raise when an exchange on this buffer timed out on any rank (the kernels then poison
+        every rank's buffer and return NaN instead of hanging the GPU)."""
+        if int(self.buf[-1].item()) != 0:
+            raise RuntimeError(
+                "vegasflow_b200: a peer-memory exchange timed out (a rank is missing, crashed, or "
+                "ran a different number of iterations); results of this instance are invalid. "
+                "VEGASFLOW_B200_EXCHANGE_TIMEOUT_S sets the bound.")
 
-def make_peer_exchange(n_dim, device):
+
+def make_peer_exchange(n_dim, device, n_cubes=0):
     """PeerExchange, or None when it is disabled (VEGASFLOW_B200_EXCHANGE=nccl) or the platform
     cannot provide peer-mapped memory (then the NCCL all-reduce path is used)."""
     if world()[1] <= 1 or os.environ.get("VEGASFLOW_B200_EXCHANGE", "p2p").lower() == "nccl":
         return None
     try:
-        return PeerExchange(n_dim, device)
+        return PeerExchange(n_dim, device, n_cubes)
     except Exception as exc:  # pylint: disable=broad-except
         logger.warning("peer-memory exchange unavailable (%s); using the NCCL all-reduce", exc)
         return None

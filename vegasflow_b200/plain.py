@@ -47,9 +47,10 @@ class PlainFlow(MonteCarloFlow):
                 res, res2 = self._vec_acc[0] + res, self._vec_acc[1] + res2
             self._vec_acc = (res, res2)
             return res, res2
+        f_acc = int_result.contiguous()  # bound to a name: must outlive the enqueue below
         _lib.check(
             lib.vf_accumulate(
-                self.n_dim, n_events, _lib.ptr(xjac), _lib.ptr(int_result.contiguous()), None, 0,
+                self.n_dim, n_events, _lib.ptr(xjac), _lib.ptr(f_acc), None, 0,
                 _lib.ptr(self._sums), None, accumulate, _lib.ptr(self._workspace),
                 self._workspace.numel() * 8, _lib.stream_ptr(),
             )

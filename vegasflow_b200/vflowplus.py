@@ -2,18 +2,24 @@
 VegasFlowPlus: VEGAS+ (adaptive importance + adaptive stratified sampling),
 API of src/vegasflow/vflowplus.py (citations relative to /root/reference).
 
-The stratified event loop (generate_samples_in_hypercubes, segment sums,
-histogram) is vfp_run_event; per-cube variances, the iteration result and
-redistribute_samples are vfp_iteration_epilogue.  Hypercube coordinates are
-derived from the cube index inside the kernel (lexicographic, dim 0 most
-significant, vflowplus.py:126-128), so no [n_cubes, n_dim] table is stored.
+Built-in / CUDA integrands run whole iterations through vfp_run_iterations: the stratified
+event kernel (generate_samples_in_hypercubes, segment sums, histogram) followed by ONE tail
+kernel (histogram reduction + grid refinement, per-cube variances, iteration result,
+redistribute_samples, new event offsets).  The sample allocation n_ev and the event count stay
+on the device between iterations -- the reference's `n_events` setter + recompile
+(monte_carlo.py:187-193, vflowplus.py:163) has no counterpart and there is no host
+synchronisation per iteration.  Under torchrun the cubes are partitioned over the ranks
+(the reference is single-device, vflowplus.py:88-100).  Python-callable integrands
+go through vfp_run_event / vfp_iteration_epilogue call by call.  Hypercube coordinates are
+derived from the cube index inside the kernel (lexicographic, dim 0 most significant,
+vflowplus.py:126-128), so no [n_cubes, n_dim] table is stored.
 """
 import logging
 
 import numpy as np
 import torch
 
-from vegasflow_b200 import _lib
+from vegasflow_b200 import _lib, parallel
 from vegasflow_b200.configflow import BINS_MAX, DTYPE, MAX_NEVAL_HCUBE
 from vegasflow_b200.integrands import BuiltinIntegrand
 from vegasflow_b200.monte_carlo import sampler, wrapper
@@ -33,7 +39,8 @@ def _n_strat_for(neval_eff, n_dim):
 class VegasFlowPlus(VegasFlow):
     """Implementation of the VEGAS+ algorithm (vflowplus.py:83-247)."""
 
-    _BATCHABLE = False  # the event count changes between iterations (adaptive)
+    _BATCHABLE = True  # the (changing) event count lives on the device: vfp_run_iterations
+    _ROW = 3           # result rows: (res, sigma, n_events of the next iteration)
 
     def __init__(self, n_dim, n_events, train=True, adaptive=False, events_limit=None, **kwargs):
         # vflowplus.py:90-100
@@ -66,15 +73,9 @@ class VegasFlowPlus(VegasFlow):
         self._events_per_run = self._n_events
         self._modified_jac = 1.0 / self._n_cubes  # :139
         self._plus_state = None
+        self.events_log = []  # events evaluated by every finished iteration (whole job)
         if self._adaptive:
             logger.warning("Variable number of events requires function signatures all across")
-        from vegasflow_b200 import parallel
-
-        if parallel.world()[1] > 1:
-            logger.warning(
-                "VegasFlowPlus is single-device (like the reference): every rank runs the whole "
-                "iteration; use VegasFlow to shard events over GPUs"
-            )
 
     @property
     def xjac(self):
@@ -129,6 +130,56 @@ class VegasFlowPlus(VegasFlow):
             )
         )
         self._set_n_events_from_device()
+
+    # ------------------------------------------------------- batched iterations
+    def _run_batched(self, n_iter):
+        """`n_iter` whole iterations with ONE C-ABI call (vfp_run_iterations), the sample
+        allocation resident on the device; None for python-callable integrands."""
+        if self._builtin is None or self._vectorial:
+            return None
+        st = self._ensure_plus_state()
+        lib = _lib.load()
+        rank, world = parallel.world()
+        xchg = self._plus_exchange() if world > 1 else None
+        if xchg is None:
+            if world > 1 and not getattr(self, "_warned_unsharded", False):
+                logger.warning("peer memory unavailable: every rank runs the whole VEGAS+ "
+                               "iteration (results are identical on all ranks)")
+                self._warned_unsharded = True
+            rank, world, ptrs, first_seq = 0, 1, None, 1
+        else:
+            ptrs, first_seq = xchg.ptrs, xchg.seq + 1
+            xchg.seq += n_iter
+        rows = self._result_rows(n_iter)
+        host = self._host_ring(n_iter)
+        _lib.check(
+            lib.vfp_run_iterations(
+                self._builtin.integrand_id(), self.n_dim, self._n_strat, self._n_cubes, self._seed,
+                self._iteration, n_iter, self._rng_bits, int(bool(self.train)),
+                int(bool(self._adaptive)), self.min_neval_hcube, self._init_calls,
+                _lib.ptr(self._grid_tensor()), self._xmin_c, self._xdelta_c, _lib.ptr(st["n_ev"]),
+                _lib.ptr(st["ev_offset"]), _lib.ptr(st["ress"]), _lib.ptr(st["ress2"]),
+                _lib.ptr(st["arr_var"]), _lib.ptr(self._hist), _lib.ptr(rows), _lib.ptr(host),
+                _lib.ptr(self._workspace), self._workspace.numel() * 8, rank, world, ptrs,
+                first_seq, _lib.stream_ptr(),
+            )
+        )
+        self._iteration += n_iter
+        return rows
+
+    def _plus_exchange(self):
+        if not self._exchange_tried:
+            self._ensure_device()
+            self._exchange = parallel.make_peer_exchange(self.n_dim, self._device,
+                                                         n_cubes=self._n_cubes)
+            self._exchange_tried = True
+        return self._exchange
+
+    def _after_batch(self, host_rows):
+        # vflowplus.py:163: the event count of the next iteration, computed on the device
+        self.events_log.extend([self._n_events] + [int(r[2]) for r in host_rows[:-1]])
+        self._n_events = int(host_rows[-1][2])
+        self._events_per_run = self._n_events
 
     def _set_n_events_from_device(self):
         st = self._plus_state
@@ -211,7 +262,7 @@ class VegasFlowPlus(VegasFlow):
         scratch = torch.zeros(2 * self._n_cubes, dtype=DTYPE, device=self._device)
         self._launch_plus(self._sampling_integrand(), n, 0, scratch[: self._n_cubes],
                           scratch[self._n_cubes :], rnds=u, x=x, w=w, ind=ind)
-        f = torch.as_tensor(integrand(x, weight=w), dtype=DTYPE, device=self._device)
+        f = torch.as_tensor(integrand(x, weight=w), dtype=DTYPE, device=self._device).contiguous()
         tmp = w * f  # vflowplus.py:209
         tmp2 = tmp * tmp
         segm = torch.repeat_interleave(
@@ -221,7 +272,7 @@ class VegasFlowPlus(VegasFlow):
         st["ress2"].zero_().index_add_(0, segm, tmp2)  # :214
         _lib.check(
             lib.vf_accumulate(
-                self.n_dim, n, _lib.ptr(w), _lib.ptr(f.contiguous()), _lib.ptr(ind),
+                self.n_dim, n, _lib.ptr(w), _lib.ptr(f), _lib.ptr(ind),
                 int(bool(self.train)), _lib.ptr(self._sums), _lib.ptr(self._hist), 0,
                 _lib.ptr(self._workspace), self._workspace.numel() * 8, _lib.stream_ptr(),
             )
@@ -229,8 +280,8 @@ class VegasFlowPlus(VegasFlow):
         return st["ress"], st["ress2"], self._hist.view(self.n_dim, BINS_MAX)
 
     def run_event(self, tensorize_events=None, **kwargs):
-        """VegasFlowPlus is single-device like the reference (vflowplus.py:88-100,
-        244-247): the whole iteration is one launch, no sharding."""
+        """Call-by-call path (vflowplus.py:244-247): the whole iteration is one launch on this
+        rank (cube sharding over ranks happens in the batched path, `_run_batched`)."""
         out = self._launch_events(**kwargs)
         self._iteration += 1
         return out
@@ -243,6 +294,9 @@ class VegasFlowPlus(VegasFlow):
 
     def _iteration_content(self):
         """vflowplus.py:222-242"""
+        rows = self._run_batched(1)
+        if rows is not None:
+            return rows[0, 0], rows[0, 1]
         self.run_event()
         return self._iteration_epilogue()
 
@@ -261,6 +315,7 @@ class VegasFlowPlus(VegasFlow):
         )
         if self.train:
             self.refine_grid(arr_res2)
+        self.events_log.append(self._n_events)
         if self._adaptive:
             self._set_n_events_from_device()
         return slot[0], slot[1]
