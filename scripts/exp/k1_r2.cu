@@ -1,0 +1,270 @@
+// Experiment harness (not product code), round 2: histogram-update and division variants of the
+// fused event kernel for symgauss d=8, timed standalone on 1e8 events.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -fmad=false -std=c++17 -I include
+//        -I vegasflow_b200/csrc scripts/exp/k1_r2.cu -o scripts/exp/k1_r2
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include "vf_common.cuh"
+#include "vf_integrands.cuh"
+
+namespace vf {
+void set_error(const char*, ...) {}
+int cuda_fail(cudaError_t e, const char* w) { printf("CUDA fail %s at %s\n", cudaGetErrorString(e), w); exit(1); }
+void count_launch(int) {}
+int sm_count() { return 148; }
+}
+using namespace vf;
+
+struct Args {
+    const double* divisions; double* out; unsigned long long* counters; uint64_t ev_begin, ev_end;
+    double xjac; uint32_t iteration; PhiloxKeys pk; IntegrandConsts ic;
+};
+
+// y/0.1 in two operations: q = fma(y, 10, y*c1) with c1 = 10*(0.1^-1/10 - 1) = -10*eps.
+__device__ __forceinline__ double div_by_tenth2(double y) {
+    // 1/0.1 = 10*(1 - 5.551115123125783e-17 + ...): 0.1 = 0x3FB999999999999A = 0.1*(1+2^-54*0.4..)
+    const double t = __dmul_rn(y, -5.5511151231257827e-16);
+    return __fma_rn(y, 10.0, t);
+}
+
+enum { H_BASE = 0, H_ROT2 = 1, H_TIGHT = 2, H_COUNT = 3, H_ROT2_TIGHT = 4, H_NONE = 5, H_NOCAS = 6, H_NATIVE = 7, H_CAS4 = 8 };
+
+template <int NDIM, int HC, int HV>
+__device__ __forceinline__ void hist_update_v(char* hist_lane, char* hist_lo, char* hist_hi, bool hi_half,
+                                              const int (&bin)[NDIM], double tmp2,
+                                              unsigned long long* counters) {
+    constexpr int S = kBins * HC * 8;  // bytes per dimension
+    if (HV == H_NONE) return;
+    if (HV == H_NOCAS) {  // racy plain RMW: lower bound on the cost of any shared-memory scheme
+#pragma unroll
+        for (int j = 0; j < NDIM; ++j) {
+            double* a = reinterpret_cast<double*>(hist_lane + j * S + bin[j] * (HC * 8));
+            *a = *a + tmp2;
+        }
+        return;
+    }
+    if (HV == H_NATIVE) {  // the compiler's own CAST.SPIN loop per dimension
+#pragma unroll
+        for (int j = 0; j < NDIM; ++j)
+            atomicAdd(reinterpret_cast<double*>(hist_lane + j * S + bin[j] * (HC * 8)), tmp2);
+        return;
+    }
+    if (HV == H_CAS4) {  // two groups of four dimensions, no rotation
+#pragma unroll
+        for (int g = 0; g < NDIM; g += 4) {
+            unsigned long long* addr[4]; unsigned long long old[4], seen[4]; unsigned long long lost = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                addr[k] = reinterpret_cast<unsigned long long*>(hist_lane + (g + k) * S + bin[g + k] * (HC * 8));
+                old[k] = *reinterpret_cast<volatile unsigned long long*>(addr[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const double upd = __longlong_as_double((long long)old[k]) + tmp2;
+                seen[k] = atomicCAS(addr[k], old[k], (unsigned long long)__double_as_longlong(upd));
+                lost |= seen[k] ^ old[k];
+            }
+            if (lost) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (seen[k] != old[k]) atomicAdd(reinterpret_cast<double*>(addr[k]), tmp2);
+            }
+        }
+        return;
+    }
+    if (HV == H_BASE || HV == H_COUNT) {
+        unsigned long long* addr[NDIM]; unsigned long long old[NDIM], seen[NDIM]; unsigned long long lost = 0;
+#pragma unroll
+        for (int j = 0; j < NDIM; ++j) {
+            addr[j] = reinterpret_cast<unsigned long long*>(hist_lane + j * S + bin[j] * (HC * 8));
+            old[j] = *reinterpret_cast<volatile unsigned long long*>(addr[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < NDIM; ++j) {
+            const double upd = __longlong_as_double((long long)old[j]) + tmp2;
+            seen[j] = atomicCAS(addr[j], old[j], (unsigned long long)__double_as_longlong(upd));
+            lost |= seen[j] ^ old[j];
+        }
+        if (lost) {
+#pragma unroll
+            for (int j = 0; j < NDIM; ++j)
+                if (seen[j] != old[j]) {
+                    if (HV == H_COUNT) atomicAdd(&counters[0], 1ull);
+                    atomicAdd(reinterpret_cast<double*>(addr[j]), tmp2);
+                }
+        }
+        if (HV == H_COUNT && (threadIdx.x & 31) == 0) atomicAdd(&counters[1], 1ull);
+        return;
+    }
+    if (HV == H_TIGHT) {  // one dimension at a time: shortest load->CAS window
+#pragma unroll
+        for (int j = 0; j < NDIM; ++j) {
+            unsigned long long* a = reinterpret_cast<unsigned long long*>(hist_lane + j * S + bin[j] * (HC * 8));
+            const unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(a);
+            const double upd = __longlong_as_double((long long)old) + tmp2;
+            const unsigned long long seen = atomicCAS(a, old, (unsigned long long)__double_as_longlong(upd));
+            if (seen != old) atomicAdd(reinterpret_cast<double*>(a), tmp2);
+        }
+        return;
+    }
+    if (HV == H_ROT2 || HV == H_ROT2_TIGHT) {
+        // lanes 0-15 walk the dimensions 0..7, lanes 16-31 walk 4..7,0..3: the two lanes that share a
+        // histogram copy never touch the same dimension in the same half -> no intra-warp conflicts
+        static_assert(NDIM == 8, "rot2 written for 8 dimensions");
+        int rb[NDIM];
+#pragma unroll
+        for (int k = 0; k < NDIM; ++k) rb[k] = hi_half ? bin[(k + 4) & 7] : bin[k];
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            char* base = g == 0 ? hist_lo : hist_hi;  // includes +-4*S for the upper half-warp
+            unsigned long long* addr[4]; unsigned long long old[4], seen[4]; unsigned long long lost = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                addr[k] = reinterpret_cast<unsigned long long*>(base + (4 * g + k) * S + rb[4 * g + k] * (HC * 8));
+                old[k] = *reinterpret_cast<volatile unsigned long long*>(addr[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const double upd = __longlong_as_double((long long)old[k]) + tmp2;
+                seen[k] = atomicCAS(addr[k], old[k], (unsigned long long)__double_as_longlong(upd));
+                lost |= seen[k] ^ old[k];
+            }
+            if (lost) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (seen[k] != old[k]) atomicAdd(reinterpret_cast<double*>(addr[k]), tmp2);
+            }
+            __syncwarp();
+        }
+    }
+}
+
+template <int NDIM, int TC, int HC, int THREADS, int MINB, int HV, int DIVV>
+__global__ void __launch_bounds__(THREADS, MINB) kvar(const __grid_constant__ Args a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    char* tblc = reinterpret_cast<char*>(smem_raw);
+    double* hist = reinterpret_cast<double*>(smem_raw + (size_t)NDIM * kBins * TC * 16);
+    for (int i = threadIdx.x; i < NDIM * kBins * TC; i += THREADS) {
+        const int jb = i / TC; const int j = jb / kBins, b = jb - j * kBins;
+        const double x_ini = a.divisions[j * kEdges + b], x_fin = a.divisions[j * kEdges + b + 1];
+        double* e = reinterpret_cast<double*>(tblc + (size_t)i * 16);
+        e[0] = x_ini; e[1] = __dsub_rn(x_fin, x_ini);
+    }
+    for (int i = threadIdx.x; i < NDIM * kBins * HC; i += THREADS) hist[i] = 0.0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const char* tbl_lane = tblc + (lane % TC) * 16;
+    char* hist_lane = reinterpret_cast<char*>(hist) + (lane % HC) * 8;
+    constexpr int S = kBins * HC * 8;
+    const bool hi_half = lane >= 16;
+    char* hist_lo = hist_lane + (hi_half ? 4 * S : 0);
+    char* hist_hi = hist_lane - (hi_half ? 4 * S : 0);
+    double sum = 0.0, sum2 = 0.0;
+    const uint64_t stride = (uint64_t)gridDim.x * THREADS;
+    for (uint64_t n = a.ev_begin + (uint64_t)blockIdx.x * THREADS + threadIdx.x; n < a.ev_end; n += stride) {
+        double x[NDIM]; int bin[NDIM]; double w = 1.0;
+#pragma unroll
+        for (int p = 0; p < (NDIM + 1) / 2; ++p) {
+            const uint4 o = philox4x32_10((uint32_t)n, (uint32_t)(n >> 32), (uint32_t)p, a.iteration, a.pk);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int j = 2 * p + h;
+                if (j < NDIM) {
+                    const double r = h == 0 ? u52_to_uniform(o.x, o.y) : u52_to_uniform(o.z, o.w);
+                    const double xn = __dmul_rn(kFBins, __dsub_rn(1.0, r));
+                    double wfac;
+                    vegas_map_dim<TC>(xn, tbl_lane + j * (kBins * TC * 16), x[j], wfac, bin[j]);
+                    w = (j == 0) ? wfac : __dmul_rn(w, wfac);
+                }
+            }
+        }
+        w = __dmul_rn(w, a.xjac);
+        double f;
+        if (DIVV == 0) {
+            f = SymGauss::eval<NDIM>(x, a.ic);
+        } else {
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < NDIM; ++j) {
+                const double t = div_by_tenth2(__dsub_rn(x[j], 0.5));
+                const double q = __dmul_rn(t, t);
+                s = (j == 0) ? q : __dadd_rn(s, q);
+            }
+            double coef = __dadd_rn(a.ic.p[1], s);
+            coef = __dsub_rn(coef, a.ic.p[1]);
+            f = __dmul_rn(a.ic.p[0], exp_nonpositive(-coef));
+        }
+        const double tmp = __dmul_rn(w, f);
+        const double tmp2 = __dmul_rn(tmp, tmp);
+        sum += tmp; sum2 += tmp2;
+        hist_update_v<NDIM, HC, HV>(hist_lane, hist_lo, hist_hi, hi_half, bin, tmp2, a.counters);
+    }
+    sum = warp_sum(sum); sum2 = warp_sum(sum2);
+    __syncthreads();
+    if (lane == 0) { atomicAdd(&a.out[0], sum); atomicAdd(&a.out[1], sum2); }
+    for (int i = threadIdx.x; i < NDIM * kBins; i += THREADS) {
+        double t = 0; for (int c = 0; c < HC; ++c) t += hist[i * HC + c];
+        atomicAdd(&a.out[2 + i], t);
+    }
+}
+
+template <int NDIM, int TC, int HC, int THREADS, int MINB, int HV, int DIVV>
+void run(const char* name, const Args& a0, int64_t n_events, const std::vector<double>* ref = nullptr,
+         std::vector<double>* keep = nullptr) {
+    auto kern = kvar<NDIM, TC, HC, THREADS, MINB, HV, DIVV>;
+    const size_t smem = (size_t)NDIM * kBins * TC * 16 + (size_t)NDIM * kBins * HC * 8;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int occ = 0; cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, THREADS, smem);
+    if (occ < 1) { printf("%-40s does not fit (smem %zu)\n", name, smem); return; }
+    Args a = a0; a.ev_end = a.ev_begin + n_events;
+    const int blocks = 148 * occ;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 6; ++rep) {
+        cudaMemsetAsync(a.out, 0, (2 + NDIM * kBins) * 8);
+        cudaMemsetAsync(a.counters, 0, 16);
+        cudaEventRecord(e0);
+        kern<<<blocks, THREADS, smem>>>(a);
+        cudaEventRecord(e1); cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaError_t err = cudaGetLastError();
+    std::vector<double> h(2 + NDIM * kBins);
+    cudaMemcpy(h.data(), a.out, h.size() * 8, cudaMemcpyDeviceToHost);
+    unsigned long long cnt[2]; cudaMemcpy(cnt, a.counters, 16, cudaMemcpyDeviceToHost);
+    cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, kern);
+    double maxrel = 0;
+    if (ref) for (size_t i = 0; i < h.size(); ++i) { double d = fabs(h[i] - (*ref)[i]) / fmax(fabs((*ref)[i]), 1e-300); if (d > maxrel) maxrel = d; }
+    if (keep) *keep = h;
+    printf("%-40s occ=%d regs=%3d smem=%6zu  %8.3f ms  %.3e ev/s  sum=%.9f maxrel=%.1e", name, occ, fa.numRegs, smem, best,
+           n_events / (best * 1e-3), h[0], maxrel);
+    if (cnt[1]) printf("  retries/warp-event=%.3f", (double)cnt[0] / (double)cnt[1]);
+    printf(" %s\n", err == cudaSuccess ? "" : cudaGetErrorString(err));
+}
+
+int main() {
+    const int d = 8; const int64_t n = 100000000;
+    std::vector<double> div(d * kEdges);
+    for (int j = 0; j < d; ++j) for (int b = 0; b <= kBins; ++b) {
+        // a peaked grid like a trained symgauss one: bins concentrated around 1/2
+        const double u = (double)b / kBins; div[j * kEdges + b] = 0.5 + 0.5 * (2 * u - 1) * (0.2 + 0.8 * (2 * u - 1) * (2 * u - 1));
+    }
+    Args a{};
+    double* ddiv; cudaMalloc(&ddiv, div.size() * 8); cudaMemcpy(ddiv, div.data(), div.size() * 8, cudaMemcpyHostToDevice);
+    cudaMalloc(&a.out, (2 + d * kBins) * 8); cudaMalloc(&a.counters, 16);
+    a.divisions = ddiv; a.ev_begin = 0; a.xjac = 1.0 / n; a.iteration = 1; a.pk = make_philox_keys(2024);
+    a.ic.p[0] = pow(1.0 / 0.1 / sqrt(M_PI), (double)d); a.ic.p[1] = (800.0 + 1) * 800.0 / 2.0;
+    std::vector<double> ref;
+    run<8, 8, 16, 512, 2, H_BASE, 0>("base (product kernel shape)", a, n, nullptr, &ref);
+    run<8, 8, 16, 512, 2, H_NATIVE, 0>("atomicAdd per dim", a, n, &ref);
+    run<8, 8, 16, 512, 2, H_NATIVE, 1>("atomicAdd per dim + 2-op div", a, n, &ref);
+    run<8, 8, 8, 512, 2, H_NATIVE, 1>("atomicAdd HC=8 + 2-op div", a, n, &ref);
+    run<8, 4, 16, 512, 2, H_NATIVE, 1>("atomicAdd TC=4 + 2-op div", a, n, &ref);
+    run<8, 8, 16, 256, 4, H_NATIVE, 1>("atomicAdd 256x4 + 2-op div", a, n, &ref);
+    run<8, 8, 16, 1024, 1, H_NATIVE, 1>("atomicAdd 1024x1 HC=16 + 2-op div", a, n, &ref);
+    run<8, 8, 16, 384, 2, H_NATIVE, 1>("atomicAdd 384x2 + 2-op div", a, n, &ref);
+    run<8, 8, 16, 640, 1, H_NATIVE, 1>("atomicAdd 640x1 + 2-op div", a, n, &ref);
+    return 0;
+}

@@ -120,34 +120,20 @@ __device__ __forceinline__ void write_partials(double sum, double sum2, const do
 }
 
 // Histogram update of one event: hist[j][bin_j][slot] += tmp2 for every dimension
-// (vflow.py:370-387, utils.py:40-43).  Shared memory has no native fp64 add, so each update is
-// a compare-and-swap; the d loads, adds and CAS are issued back to back (independent
-// addresses) and only the lanes whose CAS lost a race -- same bin as lane+HC, or another warp
-// -- fall into the retry loop.
+// (vflow.py:370-387, utils.py:40-43).  sm_100 has no native shared-memory fp64 add: atomicAdd
+// compiles to a load / DADD / ATOMS.CAST.SPIN loop per dimension.  That plain form measured 4 %
+// faster over the whole kernel than issuing the eight loads, adds and ATOMS.CAS.64 back to back
+// with a common retry path (round 1), and faster than conflict-avoiding variants -- half-warps
+// on disjoint dimensions, one dimension at a time, 32 copies (profiles/r2_k1_variants.txt):
+// ~5.7 CAS retries per warp-event happen either way and the cost is the instruction count.
 template <int NDIM>
 __device__ __forceinline__ void hist_update(char* hist_lane, const int (&bin)[NDIM], double tmp2) {
     using C = Cfg<NDIM>;
-    unsigned long long* addr[NDIM];
-    unsigned long long old[NDIM];
 #pragma unroll
-    for (int j = 0; j < NDIM; ++j) {
-        addr[j] = reinterpret_cast<unsigned long long*>(hist_lane + j * (kBins * C::HC * 8) +
-                                                        bin[j] * (C::HC * 8));
-        old[j] = *reinterpret_cast<volatile unsigned long long*>(addr[j]);
-    }
-    unsigned long long seen[NDIM];
-    unsigned long long lost = 0;
-#pragma unroll
-    for (int j = 0; j < NDIM; ++j) {
-        const double upd = __longlong_as_double((long long)old[j]) + tmp2;
-        seen[j] = atomicCAS(addr[j], old[j], (unsigned long long)__double_as_longlong(upd));
-        lost |= seen[j] ^ old[j];
-    }
-    if (lost) {
-#pragma unroll
-        for (int j = 0; j < NDIM; ++j)
-            if (seen[j] != old[j]) atomicAdd(reinterpret_cast<double*>(addr[j]), tmp2);
-    }
+    for (int j = 0; j < NDIM; ++j)
+        atomicAdd(reinterpret_cast<double*>(hist_lane + j * (kBins * C::HC * 8) +
+                                            bin[j] * (C::HC * 8)),
+                  tmp2);
 }
 
 // ---------------------------------------------------------------------------

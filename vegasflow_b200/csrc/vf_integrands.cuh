@@ -13,14 +13,18 @@ namespace vf {
 // consts.p[0] = pref = (1/a/sqrt(pi))^d, consts.p[1] = C = sum_{i<=100d} i.
 // The literal "+C ... -C" is kept: it quantises coef to ulp(C).
 // ---------------------------------------------------------------------------
-// y / 0.1 with IEEE round-to-nearest in three fp64 operations instead of the ~14 of the
-// generic division: q0 = rn(10*y) is within 1 ulp of y/a (10 = rn(1/a) and 1/a = 10*(1-2^-54...)),
-// the residual r = y - a*q0 is exact in one FMA, and q0 + 10*r rounds correctly (Markstein).
-// Checked against `/` on 4e8 values on the host and by the parity tests.
+// y / 0.1 with IEEE round-to-nearest in TWO fp64 operations instead of the ~14 of the generic
+// division.  a = fl(0.1) = (1 + 2^-54)/10 exactly, so y/a = 10y/(1 + 2^-54) =
+// 10y - 10y*2^-54 + 10y*2^-108 - ...; t = rn(y * (-10*2^-54)) carries the second term with a
+// rounding error <= 2^-51 ulp-units and fma(y, 10, t) adds it to the EXACT 10y with one rounding.
+// The value before that rounding is within 2^-50.4 (in units of ulp(y)) of the true quotient,
+// and no quotient n*10*2^54/(2^54+1) (n a 53-bit integer) lies that close to a rounding boundary
+// 4M: 10n*2^54 - 4M(2^54+1) = r with 0 < |r| <= 12 forces 10n = j*2^55 + 2j - r (j = 1, 2), which
+// is never divisible by 10 for r in {+-4, +-8, +-12}.  Hence the result equals `y / 0.1` for every
+// normal y.  Checked against `/` on 6e8 host samples and by the parity tests.
 __device__ __forceinline__ double div_by_tenth(double y) {
-    const double q0 = __dmul_rn(y, 10.0);
-    const double r = __fma_rn(-0.1, q0, y);
-    return __fma_rn(r, 10.0, q0);
+    const double t = __dmul_rn(y, -5.5511151231257827e-16);  // -10 * 2^-54, exact constant
+    return __fma_rn(y, 10.0, t);
 }
 
 // exp(x) for x <= 0 (symgauss always calls exp(-coef) with coef >= 0).  Cody-Waite reduction
