@@ -18,7 +18,7 @@ using namespace vf;
 
 struct Args {
     const double* divisions; double* out; unsigned long long* counters; uint64_t ev_begin, ev_end;
-    double xjac; uint32_t iteration; PhiloxKeys pk; IntegrandConsts ic;
+    double xjac; uint32_t iteration; PhiloxKeys pk; IntegrandConsts ic; Limits lim; int train;
 };
 
 // y/0.1 in two operations: q = fma(y, 10, y*c1) with c1 = 10*(0.1^-1/10 - 1) = -10*eps.
@@ -180,6 +180,11 @@ __global__ void __launch_bounds__(THREADS, MINB) kvar(const __grid_constant__ Ar
             }
         }
         w = __dmul_rn(w, a.xjac);
+        if (DIVV >= 2 && a.lim.has) {  // the product kernel's runtime integration-limits branch
+#pragma unroll
+            for (int j = 0; j < NDIM; ++j) x[j] = __dadd_rn(a.lim.xmin[j], __dmul_rn(x[j], a.lim.xdelta[j]));
+            w = __dmul_rn(w, a.lim.xdeltajac);
+        }
         double f;
         if (DIVV == 0) {
             f = SymGauss::eval<NDIM>(x, a.ic);
@@ -198,7 +203,8 @@ __global__ void __launch_bounds__(THREADS, MINB) kvar(const __grid_constant__ Ar
         const double tmp = __dmul_rn(w, f);
         const double tmp2 = __dmul_rn(tmp, tmp);
         sum += tmp; sum2 += tmp2;
-        hist_update_v<NDIM, HC, HV>(hist_lane, hist_lo, hist_hi, hi_half, bin, tmp2, a.counters);
+        if (DIVV < 3 || a.train)
+            hist_update_v<NDIM, HC, HV>(hist_lane, hist_lo, hist_hi, hi_half, bin, tmp2, a.counters);
     }
     sum = warp_sum(sum); sum2 = warp_sum(sum2);
     __syncthreads();
@@ -257,14 +263,18 @@ int main() {
     a.divisions = ddiv; a.ev_begin = 0; a.xjac = 1.0 / n; a.iteration = 1; a.pk = make_philox_keys(2024);
     a.ic.p[0] = pow(1.0 / 0.1 / sqrt(M_PI), (double)d); a.ic.p[1] = (800.0 + 1) * 800.0 / 2.0;
     std::vector<double> ref;
-    run<8, 8, 16, 512, 2, H_BASE, 0>("base (product kernel shape)", a, n, nullptr, &ref);
-    run<8, 8, 16, 512, 2, H_NATIVE, 0>("atomicAdd per dim", a, n, &ref);
-    run<8, 8, 16, 512, 2, H_NATIVE, 1>("atomicAdd per dim + 2-op div", a, n, &ref);
-    run<8, 8, 8, 512, 2, H_NATIVE, 1>("atomicAdd HC=8 + 2-op div", a, n, &ref);
-    run<8, 4, 16, 512, 2, H_NATIVE, 1>("atomicAdd TC=4 + 2-op div", a, n, &ref);
-    run<8, 8, 16, 256, 4, H_NATIVE, 1>("atomicAdd 256x4 + 2-op div", a, n, &ref);
-    run<8, 8, 16, 1024, 1, H_NATIVE, 1>("atomicAdd 1024x1 HC=16 + 2-op div", a, n, &ref);
-    run<8, 8, 16, 384, 2, H_NATIVE, 1>("atomicAdd 384x2 + 2-op div", a, n, &ref);
-    run<8, 8, 16, 640, 1, H_NATIVE, 1>("atomicAdd 640x1 + 2-op div", a, n, &ref);
+    a.train = 1;
+    run<8, 8, 16, 512, 2, H_NATIVE, 1>("512x2 TC=8 HC=16 (product)", a, n, nullptr, &ref);
+    run<8, 8, 16, 1024, 1, H_NATIVE, 1>("1024x1 TC=8  HC=16", a, n, &ref);
+    run<8, 16, 16, 1024, 1, H_NATIVE, 1>("1024x1 TC=16 HC=16", a, n, &ref);
+    run<8, 16, 32, 1024, 1, H_NATIVE, 1>("1024x1 TC=16 HC=32", a, n, &ref);
+    run<8, 8, 32, 1024, 1, H_NATIVE, 1>("1024x1 TC=8  HC=32", a, n, &ref);
+    run<8, 16, 8, 1024, 1, H_NATIVE, 1>("1024x1 TC=16 HC=8", a, n, &ref);
+    run<8, 4, 32, 1024, 1, H_NATIVE, 1>("1024x1 TC=4  HC=32", a, n, &ref);
+    run<8, 16, 32, 1024, 1, H_NONE, 1>("1024x1 TC=16 no hist", a, n);
+    run<8, 8, 16, 1024, 1, H_NONE, 1>("1024x1 TC=8 no hist", a, n);
+    run<8, 16, 32, 1024, 1, H_NOCAS, 1>("1024x1 TC=16 HC=32 racy", a, n);
+    run<8, 16, 32, 1024, 1, H_BASE, 1>("1024x1 TC=16 HC=32 hand CAS", a, n, &ref);
+    run<8, 16, 32, 1024, 1, H_NATIVE, 1>("1024x1 TC=16 HC=32 (repeat)", a, n, &ref);
     return 0;
 }

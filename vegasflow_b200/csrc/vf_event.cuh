@@ -9,39 +9,30 @@
 
 namespace vf {
 
-// Per-dimension-count launch configuration.  Shared memory per block:
+// Launch configuration per (dimension count, register class).  Shared memory per block:
 //   table  NDIM*50*TC*16 B  (x_ini, Delta) pairs, TC lane-interleaved copies
 //   hist   NDIM*50*HC*8  B  histogram, HC lane-interleaved copies
-// Interleaving by (lane % copies) makes the LDS.128 table reads (8 lanes per
-// phase) and the 64-bit histogram updates (16 lanes per phase) bank-conflict
-// free for any bin pattern, and leaves same-address collisions only between
-// lanes l and l+HC (probability 1/50 per pair).
-template <int NDIM>
-struct Cfg {
-    static constexpr int kThreads = 512;
-    static constexpr int kMinBlocks = (NDIM <= 8) ? 2 : 1;
-    // d <= 8: two 512-thread blocks per SM (2 x 102 KB at d = 8); above that the register budget
-    // allows one block, which then takes up to 192 KB (d = 20) so that the table stays
-    // conflict-free (TC = 8) and the histogram keeps >= 8 copies.
-    static constexpr int TC = 8;
-    static constexpr int HC = (NDIM <= 12) ? 16 : 8;
+// Interleaving by (lane % copies) makes the LDS.128 table reads (8 lanes per phase) and the
+// 64-bit histogram updates (16 lanes per phase) bank-conflict free for any bin pattern.
+//   d <= 8, light integrand : ONE block of 1024 threads per SM (64-register budget), 16 table
+//       copies and 32 histogram copies, i.e. one histogram copy per lane (no same-address
+//       collisions inside a warp): 205 KB at d = 8.  Measured 1.8 % faster than two blocks of
+//       512 threads with 8/16 copies (profiles/r2_k1_variants.txt).
+//   d  > 8 or a heavy integrand (matrix elements, 128-register budget): one block of 512
+//       threads; 8 table copies, 16 histogram copies up to d = 12, 8 above (192 KB at d = 20).
+template <int NDIM, bool HEAVY>
+struct CfgT {
+    static constexpr bool kWide = NDIM <= 8 && !HEAVY;
+    static constexpr int kThreads = kWide ? 1024 : 512;
+    static constexpr int kMinBlocks = 1;
+    static constexpr int TC = kWide ? 16 : 8;
+    static constexpr int HC = kWide ? 32 : ((NDIM <= 12) ? 16 : 8);
     static constexpr int kTblEntries = NDIM * kBins * TC;
     static constexpr int kHistEntries = NDIM * kBins * HC;
     static constexpr size_t kSmemBytes = (size_t)kTblEntries * 16 + (size_t)kHistEntries * 8;
 };
-// Resident blocks per SM the kernel is compiled for (register budget 64 vs 128).
 template <class I, int NDIM>
-constexpr int min_blocks() {
-    return (I::kHeavy || Cfg<NDIM>::kMinBlocks == 1) ? 1 : 2;
-}
-
-// The stratified kernel carries the cube state (coordinates, counts, per-cube sums) on top of
-// the event state.  Two resident blocks per SM (64-register budget, a few spilled words at
-// d = 8) measured faster than one spill-free block with 128 registers.
-template <class I, int NDIM>
-constexpr int plus_min_blocks() {
-    return (NDIM <= 8 && !I::kHeavy) ? 2 : 1;
-}
+using Cfg = CfgT<NDIM, I::kHeavy>;
 
 struct EventKernelArgs {
     const double* divisions;  // [NDIM][51]
@@ -57,10 +48,9 @@ struct EventKernelArgs {
 
 // Zero the histogram copies (independent of the previous kernel), wait for the previous kernel
 // of the stream (it refines `divisions`), then stage the (x_ini, Delta) pairs.
-template <int NDIM>
+template <class C>
 __device__ __forceinline__ void stage_grid(const double* __restrict__ divisions, double2* tbl,
                                            double* hist, bool zero_hist) {
-    using C = Cfg<NDIM>;
     if (zero_hist)
         for (int i = threadIdx.x; i < C::kHistEntries; i += blockDim.x) hist[i] = 0.0;
     pdl_wait();
@@ -90,10 +80,9 @@ __device__ __forceinline__ double apply_jacobians(double w, double (&x)[NDIM], d
 // Block-level tail shared by the event kernels: the two scalars are reduced in a fixed order
 // into this block's record; the histogram copies are reduced in-block and added to the global
 // accumulator with one fp64 RED per (dimension, bin).
-template <int NDIM>
+template <class C, int NDIM>
 __device__ __forceinline__ void write_partials(double sum, double sum2, const double* hist,
                                                bool with_hist, double* workspace) {
-    using C = Cfg<NDIM>;
     __shared__ double red[2][C::kThreads / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     sum = warp_sum(sum);
@@ -126,9 +115,8 @@ __device__ __forceinline__ void write_partials(double sum, double sum2, const do
 // with a common retry path (round 1), and faster than conflict-avoiding variants -- half-warps
 // on disjoint dimensions, one dimension at a time, 32 copies (profiles/r2_k1_variants.txt):
 // ~5.7 CAS retries per warp-event happen either way and the cost is the instruction count.
-template <int NDIM>
+template <class C, int NDIM>
 __device__ __forceinline__ void hist_update(char* hist_lane, const int (&bin)[NDIM], double tmp2) {
-    using C = Cfg<NDIM>;
 #pragma unroll
     for (int j = 0; j < NDIM; ++j)
         atomicAdd(reinterpret_cast<double*>(hist_lane + j * (kBins * C::HC * 8) +
@@ -140,17 +128,21 @@ __device__ __forceinline__ void hist_update(char* hist_lane, const int (&bin)[ND
 // K1: fused event kernel (VegasFlow._run_event, vflow.py:389-430; PlainFlow
 // plain.py:18-35).  Thread t evaluates global events ev_begin + t, + stride...
 // ---------------------------------------------------------------------------
-template <class I, int NDIM, int MODE, int RB>
-__global__ void __launch_bounds__(Cfg<NDIM>::kThreads, min_blocks<I, NDIM>())
+// FAST = the training iteration on the unit hypercube (train != 0, no integration limits): the
+// two launch-uniform branches of the generic kernel are compiled out (2 % of the kernel time --
+// they fence the instruction scheduler; profiles/r2_k1_variants.txt).  The host picks it.
+template <class I, int NDIM, int MODE, int RB, bool FAST = false>
+__global__ void __launch_bounds__(Cfg<I, NDIM>::kThreads, 1)
 event_kernel(const __grid_constant__ EventKernelArgs a) {
-    using C = Cfg<NDIM>;
+    using C = Cfg<I, NDIM>;
+    static_assert(!FAST || MODE == VF_MODE_VEGAS, "the fast path is the VEGAS training iteration");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2* tbl = reinterpret_cast<double2*>(smem_raw);
     double* hist = reinterpret_cast<double*>(smem_raw + (size_t)C::kTblEntries * 16);
-    const bool do_hist = (MODE == VF_MODE_VEGAS) && a.train;
+    const bool do_hist = FAST || ((MODE == VF_MODE_VEGAS) && a.train);
     pdl_launch_dependents();  // the reduce/refine kernel may get resident behind this grid
     if (MODE == VF_MODE_VEGAS) {
-        stage_grid<NDIM>(a.divisions, tbl, hist, do_hist);
+        stage_grid<C>(a.divisions, tbl, hist, do_hist);
         __syncthreads();
     } else {
         pdl_wait();  // the previous tail kernel still reads the per-block records
@@ -187,15 +179,16 @@ event_kernel(const __grid_constant__ EventKernelArgs a) {
                 }
             }
         }
-        w = apply_jacobians<NDIM>(w, x, a.xjac, a.lim);
+        if (FAST) w = __dmul_rn(w, a.xjac);  // monte_carlo.py:270, no limits
+        else w = apply_jacobians<NDIM>(w, x, a.xjac, a.lim);
         const double f = I::template eval<NDIM>(x, a.ic);  // vflow.py:412
         const double tmp = __dmul_rn(w, f);                // vflow.py:416
         const double tmp2 = __dmul_rn(tmp, tmp);           // vflow.py:417
         sum += tmp;                                        // vflow.py:420
         sum2 += tmp2;                                      // vflow.py:421
-        if (do_hist) hist_update<NDIM>(hist_lane, bin, tmp2);
+        if (do_hist) hist_update<C, NDIM>(hist_lane, bin, tmp2);
     }
-    write_partials<NDIM>(sum, sum2, hist, do_hist, a.partials);
+    write_partials<C, NDIM>(sum, sum2, hist, do_hist, a.partials);
 }
 
 // ---------------------------------------------------------------------------
@@ -215,13 +208,13 @@ struct DigestKernelArgs {
 };
 
 template <class I, int NDIM, int MODE>
-__global__ void __launch_bounds__(Cfg<NDIM>::kThreads, min_blocks<I, NDIM>())
+__global__ void __launch_bounds__(Cfg<I, NDIM>::kThreads, 1)
 digest_kernel(const __grid_constant__ DigestKernelArgs a) {
-    using C = Cfg<NDIM>;
+    using C = Cfg<I, NDIM>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2* tbl = reinterpret_cast<double2*>(smem_raw);
     if (MODE == VF_MODE_VEGAS) {
-        stage_grid<NDIM>(a.divisions, tbl, nullptr, false);
+        stage_grid<C>(a.divisions, tbl, nullptr, false);
         __syncthreads();
     }
     const char* tbl_lane = reinterpret_cast<const char*>(tbl) + ((threadIdx.x & 31) % C::TC) * 16;
@@ -288,15 +281,15 @@ struct PlusKernelArgs {
 };
 
 template <class I, int NDIM, bool EXT, int RB>
-__global__ void __launch_bounds__(Cfg<NDIM>::kThreads, plus_min_blocks<I, NDIM>())
+__global__ void __launch_bounds__(Cfg<I, NDIM>::kThreads, 1)
 plus_event_kernel(const __grid_constant__ PlusKernelArgs a) {
-    using C = Cfg<NDIM>;
+    using C = Cfg<I, NDIM>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2* tbl = reinterpret_cast<double2*>(smem_raw);
     double* hist = reinterpret_cast<double*>(smem_raw + (size_t)C::kTblEntries * 16);
     const bool do_hist = a.train != 0;
     pdl_launch_dependents();
-    stage_grid<NDIM>(a.divisions, tbl, hist, do_hist);  // waits for the previous tail kernel
+    stage_grid<C>(a.divisions, tbl, hist, do_hist);  // waits for the previous tail kernel
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const char* tbl_lane = reinterpret_cast<const char*>(tbl) + (lane % C::TC) * 16;
@@ -380,7 +373,7 @@ plus_event_kernel(const __grid_constant__ PlusKernelArgs a) {
         const double tmp2 = __dmul_rn(tmp, tmp);  // vflowplus.py:210
         s1 += tmp;
         s2 += tmp2;
-        if (do_hist) hist_update<NDIM>(hist_lane, bin, tmp2);
+        if (do_hist) hist_update<C, NDIM>(hist_lane, bin, tmp2);
         if (EXT) {
 #pragma unroll
             for (int j = 0; j < NDIM; ++j) {
@@ -396,7 +389,7 @@ plus_event_kernel(const __grid_constant__ PlusKernelArgs a) {
         atomicAdd(&a.ress2[cube], s2);
     }
     // per-cube sums went to ress/ress2; the block record carries no scalars here
-    write_partials<NDIM>(0.0, 0.0, hist, do_hist, a.partials);
+    write_partials<C, NDIM>(0.0, 0.0, hist, do_hist, a.partials);
 }
 
 // ---------------------------------------------------------------------------
@@ -448,10 +441,10 @@ inline int grid_blocks_for(int64_t n_events, int threads, int min_blocks_per_sm)
     return (int)want;
 }
 
-template <class I, int NDIM, int MODE, int RB>
+template <class I, int NDIM, int MODE, int RB, bool FAST = false>
 int launch_event_dim(const EventLaunch& L) {
-    using C = Cfg<NDIM>;
-    auto kern = event_kernel<I, NDIM, MODE, RB>;
+    using C = Cfg<I, NDIM>;
+    auto kern = event_kernel<I, NDIM, MODE, RB, FAST>;
     const size_t smem = MODE == VF_MODE_VEGAS ? C::kSmemBytes : 0;
     // opt in to > 48 KB dynamic shared memory once per device (the attribute is per device)
     static std::atomic<uint64_t> configured{0};
@@ -462,7 +455,7 @@ int launch_event_dim(const EventLaunch& L) {
         configured.fetch_or(1ull << dev, std::memory_order_release);
     }
     const int64_t n = (int64_t)(L.k.ev_end - L.k.ev_begin);
-    const int blocks = grid_blocks_for(n, C::kThreads, min_blocks<I, NDIM>());
+    const int blocks = grid_blocks_for(n, C::kThreads, 1);
     timing_begin(L.stream);
     VF_CUDA_CHECK(launch_pdl(kern, blocks, C::kThreads, smem, L.stream, L.k));
     timing_end(L.stream);
@@ -473,7 +466,7 @@ int launch_event_dim(const EventLaunch& L) {
 
 template <class I, int NDIM, int MODE>
 int launch_digest_dim(const DigestLaunch& L) {
-    using C = Cfg<NDIM>;
+    using C = Cfg<I, NDIM>;
     auto kern = digest_kernel<I, NDIM, MODE>;
     // opt in to > 48 KB dynamic shared memory once per device (the attribute is per device)
     static std::atomic<uint64_t> configured{0};
@@ -483,7 +476,7 @@ int launch_digest_dim(const DigestLaunch& L) {
                                            (int)C::kSmemBytes));
         configured.fetch_or(1ull << dev, std::memory_order_release);
     }
-    const int blocks = grid_blocks_for(L.k.n, C::kThreads, min_blocks<I, NDIM>());
+    const int blocks = grid_blocks_for(L.k.n, C::kThreads, 1);
     kern<<<blocks, C::kThreads, C::kSmemBytes, L.stream>>>(L.k);
     count_launch();
     VF_CUDA_CHECK(cudaGetLastError());
@@ -492,7 +485,7 @@ int launch_digest_dim(const DigestLaunch& L) {
 
 template <class I, int NDIM>
 int launch_plus_dim(const PlusLaunch& L) {
-    using C = Cfg<NDIM>;
+    using C = Cfg<I, NDIM>;
     const bool ext = L.k.rnds != nullptr;
     auto kern = ext ? plus_event_kernel<I, NDIM, true, 52>
                     : (L.rng_bits == 32 ? plus_event_kernel<I, NDIM, false, 32>
@@ -507,8 +500,8 @@ int launch_plus_dim(const PlusLaunch& L) {
     }
     // device-resident event count (n_events < 0): always the full grid, idle blocks exit at once
     const int blocks = L.k.n_events >= 0
-                           ? grid_blocks_for(L.k.n_events, C::kThreads, plus_min_blocks<I, NDIM>())
-                           : sm_count() * plus_min_blocks<I, NDIM>();
+                           ? grid_blocks_for(L.k.n_events, C::kThreads, 1)
+                           : sm_count() * 1;
     timing_begin(L.stream);
     VF_CUDA_CHECK(launch_pdl(kern, blocks, C::kThreads, C::kSmemBytes, L.stream, L.k));
     timing_end(L.stream);
@@ -520,6 +513,9 @@ int launch_plus_dim(const PlusLaunch& L) {
 // Instantiates launch_event/launch_digest/launch_plus/supported_dim for integrand I.
 #define VF_DIM_CASE_EVENT(D)                                                              \
     case D:                                                                               \
+        if (L.mode == VF_MODE_VEGAS && L.k.train && !L.k.lim.has)                         \
+            return L.rng_bits == 32 ? launch_event_dim<I, D, VF_MODE_VEGAS, 32, true>(L)  \
+                                    : launch_event_dim<I, D, VF_MODE_VEGAS, 52, true>(L); \
         if (L.rng_bits == 32)                                                             \
             return L.mode == VF_MODE_VEGAS ? launch_event_dim<I, D, VF_MODE_VEGAS, 32>(L) \
                                            : launch_event_dim<I, D, VF_MODE_PLAIN, 32>(L); \
