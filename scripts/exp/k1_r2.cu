@@ -108,10 +108,9 @@ __device__ __forceinline__ void hist_update_v(char* hist_lane, char* hist_lo, ch
         }
         return;
     }
-    if (HV == H_ROT2 || HV == H_ROT2_TIGHT) {
+    if constexpr (NDIM == 8) if (HV == H_ROT2 || HV == H_ROT2_TIGHT) {
         // lanes 0-15 walk the dimensions 0..7, lanes 16-31 walk 4..7,0..3: the two lanes that share a
         // histogram copy never touch the same dimension in the same half -> no intra-warp conflicts
-        static_assert(NDIM == 8, "rot2 written for 8 dimensions");
         int rb[NDIM];
 #pragma unroll
         for (int k = 0; k < NDIM; ++k) rb[k] = hi_half ? bin[(k + 4) & 7] : bin[k];
@@ -250,7 +249,35 @@ void run(const char* name, const Args& a0, int64_t n_events, const std::vector<d
     printf(" %s\n", err == cudaSuccess ? "" : cudaGetErrorString(err));
 }
 
-int main() {
+template <int D>
+void sweep_dim(int64_t n) {
+    std::vector<double> div(D * kEdges);
+    for (int j = 0; j < D; ++j) for (int b = 0; b <= kBins; ++b) {
+        const double u = (double)b / kBins; div[j * kEdges + b] = 0.5 + 0.5 * (2 * u - 1) * (0.2 + 0.8 * (2 * u - 1) * (2 * u - 1));
+    }
+    Args a{};
+    double* ddiv; cudaMalloc(&ddiv, div.size() * 8); cudaMemcpy(ddiv, div.data(), div.size() * 8, cudaMemcpyHostToDevice);
+    cudaMalloc(&a.out, (2 + D * kBins) * 8); cudaMalloc(&a.counters, 16);
+    a.divisions = ddiv; a.ev_begin = 0; a.xjac = 1.0 / n; a.iteration = 1; a.pk = make_philox_keys(2024); a.train = 1;
+    a.ic.p[0] = pow(1.0 / 0.1 / sqrt(M_PI), (double)D); a.ic.p[1] = (100.0 * D + 1) * (100.0 * D) / 2.0;
+    std::vector<double> ref;
+    printf("---- d = %d, %lld events\n", D, (long long)n);
+    run<D, 8, (D <= 12 ? 16 : 8), 512, 1, H_NATIVE, 1>("512x1 (round-1 config)", a, n, nullptr, &ref);
+    run<D, 4, 8, 1024, 1, H_NATIVE, 1>("1024x1 TC=4 HC=8", a, n, &ref);
+    run<D, 4, 16, 1024, 1, H_NATIVE, 1>("1024x1 TC=4 HC=16", a, n, &ref);
+    run<D, 4, 32, 1024, 1, H_NATIVE, 1>("1024x1 TC=4 HC=32", a, n, &ref);
+    run<D, 8, 8, 1024, 1, H_NATIVE, 1>("1024x1 TC=8 HC=8", a, n, &ref);
+    run<D, 8, 16, 1024, 1, H_NATIVE, 1>("1024x1 TC=8 HC=16", a, n, &ref);
+    run<D, 8, 32, 1024, 1, H_NATIVE, 1>("1024x1 TC=8 HC=32", a, n, &ref);
+    run<D, 16, 16, 1024, 1, H_NATIVE, 1>("1024x1 TC=16 HC=16", a, n, &ref);
+    run<D, 16, 32, 1024, 1, H_NATIVE, 1>("1024x1 TC=16 HC=32", a, n, &ref);
+    run<D, 4, 16, 768, 1, H_NATIVE, 1>("768x1 TC=4 HC=16", a, n, &ref);
+    run<D, 2, 16, 1024, 1, H_NATIVE, 1>("1024x1 TC=2 HC=16", a, n, &ref);
+    cudaFree(ddiv); cudaFree(a.out); cudaFree(a.counters);
+}
+
+int main(int argc, char** argv) {
+    if (argc > 1) { sweep_dim<20>(50000000); sweep_dim<16>(50000000); sweep_dim<12>(50000000); sweep_dim<9>(50000000); sweep_dim<6>(50000000); sweep_dim<4>(50000000); return 0; }
     const int d = 8; const int64_t n = 100000000;
     std::vector<double> div(d * kEdges);
     for (int j = 0; j < d; ++j) for (int b = 0; b <= kBins; ++b) {

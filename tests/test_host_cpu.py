@@ -260,6 +260,97 @@ def test_two_rank_sharding_matches_single_rank_gloo(tmp_path):
     np.testing.assert_allclose(r0[d * 50 + 2 :], co.refine_grid(hist, grid).reshape(-1), atol=1e-12)
 
 
+def test_cube_shard_partitions_cubes_exactly():
+    rng = np.random.default_rng(7)
+    for n_cubes in (1, 5, 81, 6561):
+        n_ev = rng.integers(2, 5000, size=n_cubes)
+        off = np.concatenate([[0], np.cumsum(n_ev)])
+        for world in (1, 2, 3, 8):
+            parts = [parallel.cube_shard(off, r, world) for r in range(world)]
+            assert parts[0][0] == 0 and parts[-1][1] == n_cubes
+            for (a, b), (c, d) in zip(parts, parts[1:]):
+                assert b == c and a <= b
+            # balanced on events to within one cube
+            ev = [off[b] - off[a] for a, b in parts]
+            assert max(ev) - min(ev) <= 2 * n_ev.max()
+
+
+def _gloo_plus_worker(rank, world, port, d, n_req, out_dir):
+    import torch.distributed as dist
+
+    from oracle import c_oracle as co
+    from oracle import vegas_ref as R
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        st = R.plus_setup(d, n_req, adaptive=True)
+        n_ev, grid = st["n_ev"].copy(), R.initial_divisions(d)
+        n_cubes = st["n_cubes"]
+        out = []
+        for it in range(2):
+            off = np.concatenate([[0], np.cumsum(n_ev.astype(np.int64))])
+            lo, hi = parallel.cube_shard(off)
+            mine = np.zeros_like(n_ev)
+            mine[lo:hi] = n_ev[lo:hi]
+            # stand-in for this rank's CUDA launch: the oracle on the events of its cube range,
+            # fed the slice of the GLOBAL Philox stream that belongs to those events
+            rnds = co.uniforms(9, it, int(off[lo]), int(off[hi] - off[lo]), d)
+            cubes = R.hypercube_coords(st["n_strat"], d)
+            # weights divide by the true n_ev of the cube: evaluate with the masked allocation
+            # for the event list and the true one for the weights
+            ress, _, hist, det = R.plus_run_event(rnds, st["n_strat"], mine, cubes, grid,
+                                                  R.symgauss, st["xjac"])
+            fn = n_ev.astype(np.float64)
+            ress2 = np.zeros(n_cubes)
+            np.add.at(ress2, det["segm"], det["wf"] ** 2)
+            var = np.where(mine > 0, ress2 * fn - ress * ress, 0.0)
+            t_var = torch.from_numpy(var.copy())
+            dist.all_reduce(t_var)  # disjoint supports: the sum IS the all-gather
+            sig2_part = float(np.sum(np.maximum(var, 0.0)[lo:hi] / (fn[lo:hi] - 1.0)))
+            packed = torch.from_numpy(np.concatenate([hist.reshape(-1),
+                                                      [float(ress.sum()), sig2_part]]))
+            parallel.allreduce_sum_(packed)
+            n_ev, _ = R.plus_redistribute(t_var.numpy(), st["min_neval_hcube"], st["init_calls"])
+            grid = R.refine_grid(packed[: d * 50].numpy().reshape(d, 50), grid)
+            out.append(np.concatenate([packed.numpy()[-2:], n_ev.astype(np.float64),
+                                       grid.reshape(-1)]))
+        np.save(os.path.join(out_dir, f"plus_rank{rank}.npy"), np.concatenate(out))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_vegasflowplus_cube_sharding_gloo(tmp_path):
+    """World-size-2 gloo run of the VEGAS+ multi-GPU logic (cube_shard + all-reduce of the
+    histogram and the partial (res, sigma^2) + all-gather of the per-cube variances + redundant
+    redistribute): both ranks end with identical n_ev and grids, equal to the single-rank
+    iteration on the same global Philox event space."""
+    import torch.multiprocessing as mp
+
+    from oracle import c_oracle as co
+    from oracle import vegas_ref as R
+
+    d, n_req, world = 3, 6000, 2
+    port = 29600 + (os.getpid() % 2000)
+    mp.spawn(_gloo_plus_worker, args=(world, port, d, n_req, str(tmp_path)), nprocs=world,
+             join=True)
+    r0 = np.load(tmp_path / "plus_rank0.npy")
+    r1 = np.load(tmp_path / "plus_rank1.npy")
+    np.testing.assert_array_equal(r0, r1)
+    _, _, results, grid, n_ev = R.plus_integrate(
+        R.symgauss, d, n_req, 2, lambda n, dd, iteration=0, offset=0: co.uniforms(9, iteration,
+                                                                                  offset, n, dd),
+        adaptive=True)
+    n_cubes = len(n_ev)
+    rec = 2 + n_cubes + d * 51
+    last = r0[rec:]
+    assert abs(last[0] - results[1][0]) <= 1e-12 * abs(results[1][0])
+    assert abs(np.sqrt(last[1]) - results[1][1]) <= 1e-10 * results[1][1]
+    np.testing.assert_array_equal(last[2 : 2 + n_cubes].astype(np.int32), n_ev)
+    np.testing.assert_allclose(last[2 + n_cubes :], grid.reshape(-1), atol=1e-12)
+
+
 USER_SYMGAUSS = r"""
 __device__ double integrand(const double* x, int n_dim) {
     // examples/simgauss_cffi.py:25-47 restated as a CUDA device function

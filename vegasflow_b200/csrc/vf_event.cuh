@@ -12,24 +12,31 @@ namespace vf {
 // Launch configuration per (dimension count, register class).  Shared memory per block:
 //   table  NDIM*50*TC*16 B  (x_ini, Delta) pairs, TC lane-interleaved copies
 //   hist   NDIM*50*HC*8  B  histogram, HC lane-interleaved copies
-// Interleaving by (lane % copies) makes the LDS.128 table reads (8 lanes per phase) and the
-// 64-bit histogram updates (16 lanes per phase) bank-conflict free for any bin pattern.
-//   d <= 8, light integrand : ONE block of 1024 threads per SM (64-register budget), 16 table
-//       copies and 32 histogram copies, i.e. one histogram copy per lane (no same-address
-//       collisions inside a warp): 205 KB at d = 8.  Measured 1.8 % faster than two blocks of
-//       512 threads with 8/16 copies (profiles/r2_k1_variants.txt).
-//   d  > 8 or a heavy integrand (matrix elements, 128-register budget): one block of 512
-//       threads; 8 table copies, 16 histogram copies up to d = 12, 8 above (192 KB at d = 20).
+// Interleaving by (lane % copies) keeps the LDS.128 table reads and the 64-bit histogram
+// updates bank-conflict free for any bin pattern (TC >= 8, HC >= 16).
+// ONE block per SM for every shape; measured on B200 (profiles/r2_k1_variants.txt):
+//   * 1024 threads with the 64-register budget beat 512 threads with 128 registers for every
+//     light integrand (-10 % at d = 9 ... 16; -2 % against two 512-thread blocks at d <= 8);
+//     768 threads (85 registers) are 3 % better at d >= 19, where 64 registers spill too much;
+//   * histogram copies are what the shared-memory atomics need most: HC = 32 (one copy per
+//     lane, no same-address collisions inside a warp) wherever it fits, else 16; the table gets
+//     what is left of the 227 KB (TC = 16 up to d = 8, 8 up to d = 12 and d = 15 ... 18, else 4);
+//   * heavy integrands (matrix elements) keep 512 threads and the 128-register budget.
+constexpr size_t kSmemBudget = 227 * 1024 - 2048;  // opt-in limit minus static + reserved
+constexpr size_t cfg_smem_bytes(int n_dim, int tc, int hc) {
+    return (size_t)n_dim * kBins * (16 * tc + 8 * hc);
+}
 template <int NDIM, bool HEAVY>
 struct CfgT {
-    static constexpr bool kWide = NDIM <= 8 && !HEAVY;
-    static constexpr int kThreads = kWide ? 1024 : 512;
-    static constexpr int kMinBlocks = 1;
-    static constexpr int TC = kWide ? 16 : 8;
-    static constexpr int HC = kWide ? 32 : ((NDIM <= 12) ? 16 : 8);
+    static constexpr int kThreads = HEAVY ? 512 : (NDIM >= 19 ? 768 : 1024);
+    static constexpr int HC = cfg_smem_bytes(NDIM, 4, 32) <= kSmemBudget ? 32 : 16;
+    static constexpr int TC = (NDIM <= 8 && cfg_smem_bytes(NDIM, 16, HC) <= kSmemBudget)
+                                  ? 16
+                                  : (cfg_smem_bytes(NDIM, 8, HC) <= kSmemBudget ? 8 : 4);
     static constexpr int kTblEntries = NDIM * kBins * TC;
     static constexpr int kHistEntries = NDIM * kBins * HC;
-    static constexpr size_t kSmemBytes = (size_t)kTblEntries * 16 + (size_t)kHistEntries * 8;
+    static constexpr size_t kSmemBytes = cfg_smem_bytes(NDIM, TC, HC);
+    static_assert(kSmemBytes <= kSmemBudget, "n_dim too large for the fused kernels");
 };
 template <class I, int NDIM>
 using Cfg = CfgT<NDIM, I::kHeavy>;

@@ -34,6 +34,27 @@ def shard_range(n_events, rank=None, world_size=None):
     return begin, end
 
 
+def cube_shard(ev_offset, rank=None, world_size=None):
+    """VEGAS+ over several GPUs: cube range [c_lo, c_hi) owned by `rank`.
+
+    `ev_offset` is the exclusive prefix sum of n_ev (n_cubes + 1 entries, events are ordered by
+    cube, vflowplus.py:67).  Rank r owns the cubes from the first one starting at or after event
+    n*r/R up to the first one starting at or after n*(r+1)/R: contiguous, balanced on the event
+    count to within one cube, and a pure function of the offsets -- every rank derives the same
+    partition without communicating.  Host-side mirror of `first_cube_at_or_after` in
+    csrc/vf_common.cuh (the kernels compute it on the device); used by the CPU tests.
+    """
+    import numpy as np
+
+    if rank is None or world_size is None:
+        rank, world_size = world()
+    off = np.asarray(ev_offset, dtype=np.int64)
+    n = int(off[-1])
+    lo = int(np.searchsorted(off, n * rank // world_size, side="left"))
+    hi = int(np.searchsorted(off, n * (rank + 1) // world_size, side="left"))
+    return lo, hi
+
+
 def allreduce_sum_(packed):
     """In-place SUM all-reduce of the packed per-iteration buffer (no-op for one rank)."""
     if world()[1] > 1:
