@@ -301,6 +301,8 @@ class Bench:
         step_s = self.agree_max((time.perf_counter() - t0) / W)
         self.run_steps(inst, int(min(2000, max(0, 0.3 / max(step_s, 1e-6)))))
         self.barrier()
+        if K is None:  # sub-table entries: enough steps for ~5 ms of timed work, 10 ... 200
+            K = int(min(200, max(10, 5e-3 / max(step_s, 1e-6))))
 
         sampler = ClockSampler(torch.cuda.current_device()) if clocks else None
         ev0 = torch.cuda.Event(enable_timing=True)
@@ -349,7 +351,7 @@ class Bench:
         achieved = per_gpu_events_pass2 * f_alg / (kern_ms * 1e-3) / 1e12
         return dict(inst=inst, ms=ms, events_done=events_done, launches=launches,
                     kern_ms=kern_ms, kern_n=kn.value, epi_ms=epi_ms, clocks=clk, f_alg=f_alg,
-                    per_gpu_events=per_gpu_events, achieved=achieved, plus=plus,
+                    per_gpu_events=per_gpu_events, achieved=achieved, plus=plus, steps=K,
                     value=events_done / (ms * 1e-3))
 
     def measure_e2e(self, wl, K):
@@ -426,10 +428,10 @@ def main():
         for name in (TABLE_1GPU if world == 1 else TABLE_NGPU):
             if name == args.workload:
                 continue
-            t = B.measure(WORKLOADS[name], min(K, 10), 3)
+            t = B.measure(WORKLOADS[name], None, 3)
             table[name] = {
                 "workload": WORKLOADS[name]["name"], "value": t["value"], "unit": UNIT,
-                "steps": min(K, 10), "ms_per_step": t["ms"] / min(K, 10),
+                "steps": t["steps"], "ms_per_step": t["ms"] / t["steps"],
                 "events_per_step_per_gpu": t["per_gpu_events"],
                 "kernel_ms": t["kern_ms"], "epilogue_kernel_ms": t["epi_ms"],
                 "flops_per_event": t["f_alg"], "achieved_tflops": t["achieved"],

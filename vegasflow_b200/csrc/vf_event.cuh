@@ -61,12 +61,15 @@ __device__ __forceinline__ void stage_grid(const double* __restrict__ divisions,
     if (zero_hist)
         for (int i = threadIdx.x; i < C::kHistEntries; i += blockDim.x) hist[i] = 0.0;
     pdl_wait();
-    for (int i = threadIdx.x; i < C::kTblEntries; i += blockDim.x) {
-        const int jb = i / C::TC;
+    // one thread per (dimension, bin): a single round trip to L2 for the two edges, then the TC
+    // copies are written from registers
+    for (int jb = threadIdx.x; jb < C::kTblEntries / C::TC; jb += blockDim.x) {
         const int j = jb / kBins, b = jb - j * kBins;
         const double x_ini = divisions[j * kEdges + b];      // vflow.py:70
         const double x_fin = divisions[j * kEdges + b + 1];  // vflow.py:71
-        tbl[i] = make_double2(x_ini, __dsub_rn(x_fin, x_ini));  // vflow.py:73
+        const double2 e = make_double2(x_ini, __dsub_rn(x_fin, x_ini));  // vflow.py:73
+#pragma unroll
+        for (int c = 0; c < C::TC; ++c) tbl[jb * C::TC + c] = e;
     }
 }
 
@@ -108,8 +111,10 @@ __device__ __forceinline__ void write_partials(double sum, double sum2, const do
         double* acc = workspace + ws_acc_offset();
         for (int i = threadIdx.x; i < NDIM * kBins; i += blockDim.x) {
             double t = 0.0;
+            // thread i starts at copy i: the lanes of a warp read different banks (a plain
+            // c = 0.. walk has all 32 lanes on one bank: the rows are HC*8 = 256 B apart)
 #pragma unroll
-            for (int c = 0; c < C::HC; ++c) t += hist[i * C::HC + c];
+            for (int c = 0; c < C::HC; ++c) t += hist[i * C::HC + ((c + i) & (C::HC - 1))];
             atomicAdd(acc + i, t);  // RED.E.ADD.F64
         }
     }
