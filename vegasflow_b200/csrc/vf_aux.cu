@@ -106,19 +106,37 @@ __device__ __forceinline__ void sts_s32(uint32_t addr, int v) {
 
 #ifdef VF_PHASE_TIMING
 __device__ long long g_phase_clock[16];
+__device__ int g_phase_bad;
 #define VF_PHASE(k) do { if (threadIdx.x == 0 && blockIdx.x == 0) g_phase_clock[k] = clock64(); } while (0)
 #else
 #define VF_PHASE(k) do { } while (0)
 #endif
 
+// The rebinning loop of the reference (vflow.py:195-208) is one serial floating-point chain:
+// state (bin_weight, n_bin, cur, prev); 49 times { while (bin_weight < ave) advance one bin,
+// bin_weight += wei[n]; then bin_weight -= ave and one boundary is emitted }.  A lone lane
+// walking it with its data-dependent branches needs ~7.3k cycles -- most of this kernel.  Here
+// the SAME chain of additions is evaluated, bit for bit, in three steps:
+//   1. predict where every boundary falls from plain prefix sums (parallel over boundaries);
+//   2. lay the chain's operands out in order (wei[n] for an advance, -ave for an emit) and let
+//      one lane run the 99 dependent additions with no branch and no address computation;
+//   3. verify in parallel that every decision the reference would have taken on the exact
+//      running value (bin_weight < ave or not) is the predicted one.
+// A mismatch can only come from a running value within a rounding error of `ave`; then -- and
+// for the out-of-bins guard -- the serial loop below runs instead, so the result is always the
+// reference's sequence of IEEE operations.
 __device__ void refine_dimension(const double* __restrict__ t_res_sq, double* sub_global) {
-    __shared__ double sub[kEdges], sm[kBins], wei[kBins];
-    __shared__ double s_sum;
+    __shared__ double sub[kEdges], sm[kBins], wei[kBins], pre[kBins];
+    __shared__ double s_sum, s_ave;
     __shared__ double b_cur[kBins], b_prev[kBins], b_bw[kBins];
     __shared__ int b_n[kBins];
+    __shared__ double ops[2 * kBins], bwt[2 * kBins];
+    __shared__ signed char kind[2 * kBins];  // 1 = advance, 0 = emit
+    __shared__ int s_bad;
     const int i = threadIdx.x;
     VF_PHASE(2);
     if (i < kEdges) sub[i] = sub_global[i];
+    if (i == 0) s_bad = 0;
     if (i < kBins) {
         const double c = t_res_sq[i];
         const double right = i < kBins - 1 ? t_res_sq[i + 1] : 0.0;  // tf.pad, :156
@@ -148,26 +166,82 @@ __device__ void refine_dimension(const double* __restrict__ t_res_sq, double* su
     }
     __syncthreads();
     VF_PHASE(5);
-    if (i < 32) {  // the whole first warp runs the serial part redundantly: uniform branches,
-                   // no divergence barriers around every step (all lanes store identical values)
+    if (i == 0) {
         double s = 0.0;
-        for (int k = 0; k < kBins; ++k) s = __dadd_rn(s, wei[k]);
-        const double ave = __ddiv_rn(s, (double)kBins);  // :166
-        VF_PHASE(6);
-        // serial scan :195-205 (state: bin_weight, n_bin, cur, prev).  The reference advances
-        // n while bin_weight < ave and then emits one boundary; here the same sequence of
-        // additions/subtractions/comparisons is driven by n with the emits in an inner loop --
-        // identical floating-point operations in the identical order; the operands of step n+1
-        // are fetched one step ahead so no shared-memory latency sits on the dependent chain.
-        // (Measured alternatives -- speculative/branch-free steps, integer compares, explicit
-        // shared addressing -- were all slower: a lone lane issues ~1 instruction per 6-7 cycles,
-        // so the shortest instruction sequence wins; scripts/exp/epi_phases.cu.)
+        for (int k = 0; k < kBins; ++k) {
+            s = __dadd_rn(s, wei[k]);
+            pre[k] = s;  // prefix sums: used for the prediction only
+        }
+        s_ave = __ddiv_rn(s, (double)kBins);  // :166
+    }
+    __syncthreads();
+    VF_PHASE(6);
+    const double ave = s_ave;
+    // 1. predicted bin of boundary k: the first n whose prefix sum reaches k*ave
+    if (i >= 1 && i < kBins) {
+        const double target = __dmul_rn((double)i, ave);
+        int n = 0;
+#pragma unroll
+        for (int m = 0; m < kBins; ++m) n += pre[m] < target ? 1 : 0;
+        b_n[i] = n < kBins ? n : kBins - 1;
+    }
+    if (i == 0) b_n[0] = -1;
+    __syncthreads();
+    // 2. operand sequence: emit k sits after n_k + 1 advances and k - 1 emits
+    const int t_last = b_n[kBins - 1] + kBins - 1;  // position of the last emit
+    if (i >= 1 && i < kBins) {
+        const int t = b_n[i] + i;
+        ops[t] = -ave;
+        kind[t] = 0;
+    }
+    if (i < kBins) {
+        int emitted = 0;  // boundaries emitted before bin i is entered
+#pragma unroll
+        for (int k = 1; k < kBins; ++k) emitted += b_n[k] < i ? 1 : 0;
+        ops[i + emitted] = wei[i];
+        kind[i + emitted] = 1;
+    }
+    __syncthreads();
+    if (i == 0) {
+        // The reference's chain, bin_weight += wei[n] (:187) / bin_weight -= ave (:205), as 99
+        // dependent additions, fully unrolled: the operand loads carry no dependence on the
+        // running value and are issued ahead of it, so only the additions are on the chain.
+        constexpr int kSteps = 2 * kBins - 1;  // 50 advances + 49 emits
+        double bw = 0.0;
+#pragma unroll
+        for (int t = 0; t < kSteps; ++t) {
+            bw = __dadd_rn(bw, ops[t]);
+            bwt[t] = bw;
+        }
+    }
+    __syncthreads();
+    // 3. every decision, re-taken on the exact running value
+    for (int t = i; t <= t_last; t += blockDim.x) {
+        const double before = t == 0 ? 0.0 : bwt[t - 1];
+        const bool advance = before < ave;  // while_check, :170-173
+        if (advance != (kind[t] == 1)) s_bad = 1;
+    }
+    __syncthreads();
+#ifdef VF_PHASE_TIMING
+    if (i == 0 && blockIdx.x == 0) g_phase_bad = s_bad;
+#endif
+    if (!s_bad) {
+        if (i >= 1 && i < kBins) {
+            const int n = b_n[i];
+            b_cur[i] = sub[n + 1];  // :189
+            b_prev[i] = sub[n];     // :188 (the previous `cur`; sub[0] = 0 = the initial cur)
+            b_bw[i] = bwt[n + i];   // bin_weight after `-= ave`, :205
+        }
+    } else if (i < 32) {
+        // Fallback: the whole first warp walks the serial loop redundantly (uniform branches, all
+        // lanes store identical values).  Same additions/subtractions/comparisons in the same
+        // order; operands of step n+1 are fetched one step ahead.
         double bw = 0.0, cur = 0.0, prev = 0.0;
         int k = 1;
         double w_cur = wei[0], s_cur = sub[1];
 #pragma unroll 1
         for (int n = 0; n < kBins && k < kBins; ++n) {
-            const int m = n + 1 < kBins ? n + 1 : n;  // operands of the next step, fetched ahead
+            const int m = n + 1 < kBins ? n + 1 : n;
             const double w_nxt = wei[m], s_nxt = sub[m + 1];
             bw = __dadd_rn(bw, w_cur);  // :187
             prev = cur;                 // :188
