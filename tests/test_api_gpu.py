@@ -339,7 +339,7 @@ def test_batched_and_verbose_paths_agree():
     assert abs(out[0][1] - out[1][1]) <= 1e-7 * out[0][1]
 
 
-def _torchrun_dist_check(tmp_path, tag, alg, exchange, port):
+def _torchrun_dist_check(tmp_path, tag, alg, exchange, port, **extra_env):
     import json
     import os
     import subprocess
@@ -350,7 +350,7 @@ def _torchrun_dist_check(tmp_path, tag, alg, exchange, port):
     out = tmp_path / f"dist_{tag}.json"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
            "--master-addr", "127.0.0.1", "--master-port", str(port), script, str(out), alg]
-    env = dict(os.environ, VEGASFLOW_B200_EXCHANGE=exchange)
+    env = dict(os.environ, VEGASFLOW_B200_EXCHANGE=exchange, **extra_env)
     subprocess.run(cmd, check=True, timeout=600, cwd=root, env=env)
     return json.load(open(out))
 
@@ -378,6 +378,18 @@ def test_two_gpu_sharding_matches_single_gpu(tmp_path):
     res, err = inst.run_integration(4)
     data = _torchrun_dist_check(tmp_path, "plain", "plain", "p2p", 29615)
     assert abs(res - data["res"]) <= 1e-9 * abs(res) and abs(err - data["err"]) <= 1e-7 * err
+
+
+def test_two_gpu_missing_peer_poisons_instead_of_hanging(tmp_path):
+    """A rank that never joins an exchange (crash, mismatched iteration counts): the waiting rank
+    gives up after VEGASFLOW_B200_EXCHANGE_TIMEOUT_S, poisons every rank's buffer, returns NaN and
+    the host raises -- no hung GPU, no silently wrong sums (exchange_epilogue_kernel)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    data = _torchrun_dist_check(tmp_path, "timeout", "timeout", "p2p", 29619,
+                                VEGASFLOW_B200_EXCHANGE_TIMEOUT_S="2")
+    assert data["outcome"].startswith("raised"), data
+    assert data["poisoned"] == 1 and 1.5 < data["seconds"] < 30.0
 
 
 def test_two_gpu_vegasflowplus_cube_sharding_matches_single_gpu(tmp_path):
