@@ -62,26 +62,29 @@ void vfo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
-/* Two 32-bit words -> double in [TECH_CUT, 1-TECH_CUT):
+/* Two 32-bit words -> uniform double r in (TECH_CUT, 1-TECH_CUT]:
  *   m = 1.mantissa (52 bits: low 20 bits of `hi`, all of `lo`) in [1,2)
- *   r = fma(m, S, T - S)   with S = 1 - 2*TECH_CUT, T = TECH_CUT
- * i.e. r = T + (m-1)*S with a single rounding. */
+ *   v = fma(m, S, 3T)  in [1+T, 2-T)   with S = 1 - 2*TECH_CUT, T = TECH_CUT  (one rounding)
+ *   r = 2 - v          exact: r is a multiple of 2^-52
+ * so that 1 - r = v - 1 is exact as well and the fused CUDA kernel may evaluate the reference's
+ * xn = 50*(1-r) (vflow.py:117) as fma(v, 50, -50) with a bit-identical result
+ * (vegasflow_b200/csrc/vf_common.cuh::u52_to_v). */
 static inline double u52_to_uniform(uint32_t hi, uint32_t lo) {
     union { uint64_t u; double d; } v;
     v.u = ((uint64_t)(0x3FF00000u | (hi & 0xFFFFFu)) << 32) | lo;
     const double S = 1.0 - 2.0 * TECH_CUT;
-    const double C = TECH_CUT - S;
-    return fma(v.d, S, C);
+    const double C = 3.0 * TECH_CUT;
+    return 2.0 - fma(v.d, S, C);
 }
 
 /* One word -> uniform in (TECH_CUT, 1-TECH_CUT): top 32 mantissa bits, m = 1 + k*2^-32,
- *   r = fma(m, S, T - S + S*2^-33) = T + (k + 1/2) * 2^-32 * S     (optional 32-bit stream) */
+ *   v = fma(m, S, 3T + S*2^-33) = 1 + T + (k + 1/2) * 2^-32 * S,  r = 2 - v  (32-bit stream) */
 static inline double u32_to_uniform(uint32_t k) {
     union { uint64_t u; double d; } v;
     v.u = ((uint64_t)(0x3FF00000u | (k >> 12)) << 32) | (uint32_t)(k << 20);
     const double S = 1.0 - 2.0 * TECH_CUT;
-    const double C = (TECH_CUT - S) + S * 1.1641532182693481e-10; /* 2^-33 */
-    return fma(v.d, S, C);
+    const double C = 3.0 * TECH_CUT + S * 1.1641532182693481e-10; /* 2^-33 */
+    return 2.0 - fma(v.d, S, C);
 }
 
 /* Stream selection: 52 (default, two words per uniform) or 32 (one word per uniform). */

@@ -41,12 +41,40 @@ def test_philox_known_answers():
 
 def test_uniform_stream_range_and_independence_of_chunking():
     r = co.uniforms(3, 2, 0, 50000, 5)
-    assert r.min() >= R.TECH_CUT * 0.99 and r.max() < 1 - R.TECH_CUT
+    assert r.min() > R.TECH_CUT * 0.99 and r.max() <= 1 - R.TECH_CUT
     assert abs(r.mean() - 0.5) < 5e-3
     a = co.uniforms(3, 2, 1000, 100, 5)
     np.testing.assert_array_equal(a, r[1000:1100])  # counter-based: offset == slice
     assert not np.array_equal(co.uniforms(3, 3, 0, 10, 5), r[:10])  # iteration changes stream
     assert not np.array_equal(co.uniforms(4, 2, 0, 10, 5), r[:10])  # seed changes stream
+
+
+def test_uniform_stream_definition_makes_the_first_reference_steps_exact():
+    """r = 2 - v with v = fma(m, S, 3T) in [1+T, 2-T): r is a multiple of 2^-52, so 1-r (vflow.py:117)
+    is exact and rn(50*(1-r)) == rn(50*v - 50) -- what the fused kernel evaluates as ONE fma on v
+    (vf_common.cuh::u52_to_v).  Checked in exact rational arithmetic against the Philox words."""
+    from fractions import Fraction
+    seed, it, d = 11, 3, 6
+    r = co.uniforms(seed, it, 40, 64, d)
+    assert np.array_equal(r * 2.0**52, np.floor(r * 2.0**52))  # on the 2^-52 grid
+    T, S = Fraction(R.TECH_CUT), Fraction(1.0 - 2.0 * R.TECH_CUT)
+    for ev in (40, 41, 103):
+        for p in range(d // 2):
+            w = co.philox4x32_10(np.array([ev, 0, p, it], dtype=np.uint32), [seed, 0])
+            for h in range(2):
+                hi, lo = int(w[2 * h]), int(w[2 * h + 1])
+                m = 1 + Fraction(((hi & 0xFFFFF) << 32) | lo, 2**52)
+                exact_v = m * S + Fraction(3.0 * R.TECH_CUT)
+                got = Fraction(float(r[ev - 40, 2 * p + h]))
+                v = 2 - got                                   # exact by construction
+                assert abs(v - exact_v) <= Fraction(1, 2**53)  # one rounding to the grid of [1,2)
+                # the reference's first two operations on r, and the kernel's single fma on v
+                one_minus_r = 1.0 - float(got)
+                assert Fraction(one_minus_r) == 1 - got        # exact
+                xn_ref = 50.0 * one_minus_r                   # rn(50 * (1 - r))
+                exact_xn = 50 * v - 50
+                ulp = Fraction(np.spacing(xn_ref))
+                assert abs(Fraction(xn_ref) - exact_xn) <= ulp / 2  # == rn(50 v - 50), the fma
 
 
 @pytest.mark.parametrize("name,d", [("symgauss", 2), ("symgauss", 4), ("symgauss", 8),
@@ -194,7 +222,7 @@ def test_plus_integrates_to_one():
 
 
 def test_rng32_stream_definition():
-    """Optional 32-bit stream: (k + 1/2) * 2^-32 mapped into (TECH_CUT, 1-TECH_CUT)."""
+    """Optional 32-bit stream: r = (1-T) - (k + 1/2) * 2^-32 * S, inside (TECH_CUT, 1-TECH_CUT)."""
     co.set_rng_bits(32)
     try:
         r = co.uniforms(9, 0, 0, 100000, 7)
@@ -204,7 +232,7 @@ def test_rng32_stream_definition():
     finally:
         co.set_rng_bits(52)
     assert r.min() > R.TECH_CUT and r.max() < 1 - R.TECH_CUT and abs(r.mean() - 0.5) < 3e-3
-    want = R.TECH_CUT + (words[:3].astype(np.float64) + 0.5) * 2.0**-32 * (1 - 2 * R.TECH_CUT)
+    want = (1 - R.TECH_CUT) - (words[:3].astype(np.float64) + 0.5) * 2.0**-32 * (1 - 2 * R.TECH_CUT)
     np.testing.assert_allclose(row[4:7], want, rtol=0, atol=2e-16)  # dims 4..6 <- block 1
     default = co.uniforms(9, 0, 0, 100, 7)
     assert not np.array_equal(default, r[:100])

@@ -124,24 +124,39 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
     return make_uint4(c0, c1, c2, c3);
 }
 
-// Two words -> uniform double in [TECH_CUT, 1-TECH_CUT): 52-bit mantissa fill
-// m in [1,2), then r = fma(m, S, T-S) = T + (m-1)*S with one rounding.
-__device__ __forceinline__ double u52_to_uniform(uint32_t hi, uint32_t lo) {
+// ---- Philox words -> uniforms ------------------------------------------------
+// The stream is defined through v = fma(m, S, 3T) with m in [1,2) the mantissa fill,
+// S = 1 - 2*TECH_CUT, T = TECH_CUT: v lies in [1+T, 2-T), i.e. on the 2^-52 grid of that
+// binade, and the uniform handed to the reference's seam (monte_carlo.py:264-268) is
+//     r = 2 - v     in (TECH_CUT, 1-TECH_CUT],   EXACT (Sterbenz).
+// Because r is a multiple of 2^-52, everything the reference does first with r is exact too:
+//   vflow.py:117      1 - r = v - 1 exactly, so  xn = rn(50*(1-r)) = rn(50*v - 50) = fma(v, 50, -50)
+//   vflowplus.py:72   points + r = (points+2) - v in the reals, so rn(points+r) = rn((points+2) - v)
+// -- the fused kernels consume v directly and never form r: one fp64 instruction per dimension
+// less than r = fma(..), 1-r, 50*(..) (8 of the 152 fp64 instructions per event at d = 8), with
+// bit-identical xn.  Identical to oracle/vegas_oracle.c::u52_to_uniform / u32_to_uniform.
+__device__ __forceinline__ double u52_to_v(uint32_t hi, uint32_t lo) {
+    // two words, 52-bit mantissa fill (like tf.random.uniform for float64)
     const double m = __hiloint2double((int)(0x3FF00000u | (hi & 0xFFFFFu)), (int)lo);
     constexpr double S = 1.0 - 2.0 * kTechCut;
-    constexpr double C = kTechCut - S;
+    constexpr double C = 3.0 * kTechCut;  // (1 + T) - S
     return fma(m, S, C);
 }
-
-// One 32-bit word -> uniform double in (TECH_CUT, 1-TECH_CUT): the word fills the TOP 32
-// mantissa bits, m = 1 + k*2^-32, r = fma(m, S, T - S + S*2^-33) = T + (k + 1/2)*2^-32*S.
-// Optional stream (rng_bits = 32): four uniforms per Philox block instead of two, i.e. half the
-// integer-multiply work; resolution 2.3e-10 (TECH_CUT is 1e-8).  Not the default.
-__device__ __forceinline__ double u32_to_uniform(uint32_t k) {
+// One 32-bit word fills the TOP 32 mantissa bits, m = 1 + k*2^-32, and the offset puts v at the
+// middle of its cell: v = 1 + T + (k + 1/2)*2^-32*S.  Optional stream (rng_bits = 32): four
+// uniforms per Philox block instead of two, i.e. half the integer-multiply work; resolution
+// 2.3e-10 (TECH_CUT is 1e-8).  Not the default.
+__device__ __forceinline__ double u32_to_v(uint32_t k) {
     const double m = __hiloint2double((int)(0x3FF00000u | (k >> 12)), (int)(k << 20));
     constexpr double S = 1.0 - 2.0 * kTechCut;
-    constexpr double C = (kTechCut - S) + S * 1.1641532182693481e-10;  // 2^-33
+    constexpr double C = 3.0 * kTechCut + S * 1.1641532182693481e-10;  // + S*2^-33
     return fma(m, S, C);
+}
+__device__ __forceinline__ double u52_to_uniform(uint32_t hi, uint32_t lo) {
+    return __dsub_rn(2.0, u52_to_v(hi, lo));
+}
+__device__ __forceinline__ double u32_to_uniform(uint32_t k) {
+    return __dsub_rn(2.0, u32_to_v(k));
 }
 
 // Uniforms per Philox block and word selection for the two stream definitions.
@@ -149,9 +164,13 @@ template <int RB>
 struct Rng {
     static_assert(RB == 52 || RB == 32, "rng_bits is 52 or 32");
     static constexpr int kPerCall = RB == 32 ? 4 : 2;
+    // v = 2 - r of uniform h of the block (see above)
+    static __device__ __forceinline__ double v(const uint4& o, int h) {
+        if (RB == 32) return u32_to_v(h == 0 ? o.x : (h == 1 ? o.y : (h == 2 ? o.z : o.w)));
+        return h == 0 ? u52_to_v(o.x, o.y) : u52_to_v(o.z, o.w);
+    }
     static __device__ __forceinline__ double uniform(const uint4& o, int h) {
-        if (RB == 32) return u32_to_uniform(h == 0 ? o.x : (h == 1 ? o.y : (h == 2 ? o.z : o.w)));
-        return h == 0 ? u52_to_uniform(o.x, o.y) : u52_to_uniform(o.z, o.w);
+        return __dsub_rn(2.0, v(o, h));
     }
 };
 __device__ __forceinline__ double rng_uniform(const uint4& o, int h, int rng_bits) {

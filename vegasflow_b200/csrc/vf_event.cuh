@@ -178,15 +178,16 @@ event_kernel(const __grid_constant__ EventKernelArgs a) {
             for (int h = 0; h < PC; ++h) {
                 const int j = PC * p + h;
                 if (j < NDIM) {
-                    const double r = Rng<RB>::uniform(o, h);
+                    const double v = Rng<RB>::v(o, h);  // the uniform is r = 2 - v, exactly
                     if (MODE == VF_MODE_VEGAS) {
-                        const double xn = __dmul_rn(kFBins, __dsub_rn(1.0, r));  // vflow.py:117
+                        // vflow.py:117: rn(50*(1-r)) with 1-r = v-1 exact == rn(50*v - 50)
+                        const double xn = fma(v, kFBins, -kFBins);
                         double wfac;
                         vegas_map_dim<C::TC>(xn, tbl_lane + j * (kBins * C::TC * 16), x[j], wfac,
                                              bin[j]);
                         w = (j == 0) ? wfac : __dmul_rn(w, wfac);  // reduce_prod, vflow.py:78
                     } else {
-                        x[j] = r;  // monte_carlo.py:290-298
+                        x[j] = __dsub_rn(2.0, v);  // r itself, monte_carlo.py:290-298
                     }
                 }
             }
@@ -316,16 +317,27 @@ plus_event_kernel(const __grid_constant__ PlusKernelArgs a) {
         ev_hi = a.ev_offset[first_cube_at_or_after(a.ev_offset, a.n_cubes,
                                                    n_events * (a.rank + 1) / a.world)];
     }
+    // The block's slice is cut into one CONTIGUOUS range per warp, lanes striding by 32: the
+    // lanes of a warp sit in the same cube almost always and a lane walks past the end of its
+    // cube once per n_ev/32 events.  (Striding the whole block through the slice made every
+    // thread re-locate its cube every n_ev/1024 ~ 8 events at 1e8 events / 6561 cubes: search,
+    // coordinates and the two REDs were 21 % of the executed instructions,
+    // profiles/r2_prof_c3_details.txt.)
     const int64_t per_block = (ev_hi - ev_lo + gridDim.x - 1) / gridDim.x;
-    const int64_t begin = ev_lo + (int64_t)blockIdx.x * per_block;
-    const int64_t end = min(begin + per_block, ev_hi);
+    const int64_t bbegin = ev_lo + (int64_t)blockIdx.x * per_block;
+    const int64_t bend = min(bbegin + per_block, ev_hi);
+    constexpr int kWarps = C::kThreads / 32;
+    const int64_t per_warp = bend > bbegin ? (bend - bbegin + kWarps - 1) / kWarps : 0;
+    const int64_t begin = bbegin + (int64_t)(threadIdx.x >> 5) * per_warp;
+    const int64_t end = min(begin + per_warp, bend);
     const double fstrat = (double)a.n_strat;
     const double rstrat = __ddiv_rn(1.0, fstrat);
+    const uint32_t ustrat = (uint32_t)a.n_strat;
 
     int64_t cube = -1, hi = 0;
     double s1 = 0.0, s2 = 0.0, fn = 1.0, rfn = 1.0;
     double coords[NDIM];
-    for (int64_t e = begin + threadIdx.x; e < end; e += C::kThreads) {
+    for (int64_t e = begin + lane; e < end; e += 32) {
         if (e >= hi) {
             if (cube >= 0) {
                 atomicAdd(&a.ress[cube], s1);   // segment_sum, vflowplus.py:213
@@ -333,8 +345,17 @@ plus_event_kernel(const __grid_constant__ PlusKernelArgs a) {
                 s1 = 0.0;
                 s2 = 0.0;
             }
-            // largest c with ev_offset[c] <= e  (tf.repeat(arange, n_ev), vflowplus.py:67)
-            int64_t lo_c = cube < 0 ? 0 : cube + 1, hi_c = a.n_cubes;  // search in (lo_c, hi_c]
+            // largest c with ev_offset[c] <= e  (tf.repeat(arange, n_ev), vflowplus.py:67):
+            // gallop forward from the current cube (the next one, nearly always), then bisect
+            int64_t lo_c = cube < 0 ? 0 : cube + 1, hi_c = a.n_cubes;  // answer in [lo_c, hi_c)
+            if (cube >= 0) {
+                int64_t step = 1;
+                while (lo_c + step < hi_c && a.ev_offset[lo_c + step] <= e) {
+                    lo_c += step;
+                    step <<= 1;
+                }
+                hi_c = min(hi_c, lo_c + step);
+            }
             while (lo_c < hi_c - 1) {
                 const int64_t mid = (lo_c + hi_c) >> 1;
                 if (a.ev_offset[mid] <= e) lo_c = mid; else hi_c = mid;
@@ -343,11 +364,11 @@ plus_event_kernel(const __grid_constant__ PlusKernelArgs a) {
             hi = a.ev_offset[cube + 1];
             fn = (double)a.n_ev[cube];  // vflowplus.py:69
             rfn = __ddiv_rn(1.0, fn);
-            int64_t rem = cube;         // itertools.product order, vflowplus.py:126-128
+            uint32_t rem = (uint32_t)cube;  // itertools.product order, vflowplus.py:126-128
 #pragma unroll
             for (int j = NDIM - 1; j >= 0; --j) {
-                const int64_t q = rem / a.n_strat;
-                coords[j] = (double)(rem - q * a.n_strat);
+                const uint32_t q = rem / ustrat;
+                coords[j] = (double)(rem - q * ustrat + (EXT ? 0u : 2u));
                 rem = q;
             }
         }
@@ -365,12 +386,12 @@ plus_event_kernel(const __grid_constant__ PlusKernelArgs a) {
             for (int h = 0; h < PC; ++h) {
                 const int j = PC * p + h;
                 if (j < NDIM) {
-                    double r;
-                    if (EXT) r = a.rnds[e * NDIM + j];
-                    else r = Rng<RB>::uniform(o, h);
-                    // vflowplus.py:72: (points + rnds) * FBINS / n_strat
-                    const double xn =
-                        div_rn_by(__dmul_rn(__dadd_rn(coords[j], r), kFBins), fstrat, rstrat);
+                    // vflowplus.py:72: (points + rnds) * FBINS / n_strat.  On the engine's own
+                    // stream r = 2 - v exactly, and coords[] holds points + 2 (an exact small
+                    // integer): rn(points + r) == rn((points + 2) - v)
+                    const double pr = EXT ? __dadd_rn(coords[j], a.rnds[e * NDIM + j])
+                                          : __dsub_rn(coords[j], Rng<RB>::v(o, h));
+                    const double xn = div_rn_by(__dmul_rn(pr, kFBins), fstrat, rstrat);
                     double wfac;
                     vegas_map_dim<C::TC>(xn, tbl_lane + j * (kBins * C::TC * 16), x[j], wfac,
                                          bin[j]);

@@ -48,7 +48,10 @@ __device__ __forceinline__ double exp_nonpositive(double x) {
     double p = kExpCoef[11];
 #pragma unroll
     for (int i = 10; i >= 0; --i) p = fma(p, r, kExpCoef[i]);
-    if (x < -700.0) {  // result below 2^-1009: two-step scaling through the subnormal range
+    // x < -700 tested on the high word (x <= 0: the unsigned order of the words is the order of
+    // |x|; 0xC085E000 = hi(-700.0)) -- an integer compare instead of a DSETP on the fp64 pipe.
+    // For -700 - 2^-43 < x < -700 this takes the direct path, which is exact down to 2^-1022.
+    if ((uint32_t)__double2hiint(x) > 0xC085E000u) {  // two-step scaling through the subnormals
         if (x < -800.0) return 0.0;
         const double q = __hiloint2double(__double2hiint(p) + ((k + 256) << 20), __double2loint(p));
         return q * 8.636168555094445e-78;  // 2^-256
