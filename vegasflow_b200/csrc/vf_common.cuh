@@ -95,9 +95,18 @@ constexpr uint32_t kPhiloxW1 = 0xBB67AE85u;
 struct PhiloxKeys {
     uint32_t k0[10];
     uint32_t k1[10];
+    // 0x3FF00000, the exponent word of [1,2).  It travels as a launch parameter so that ptxas
+    // cannot see a constant: (word & 0xFFFFF) | expo then stays ONE LOP3 (immediate mask +
+    // register) instead of an AND and an OR with two immediates -- LOP3 holds the integer dispatch
+    // port two cycles on sm_100 (profiles/r2_pipes2.txt), and there is one per uniform.
+    uint32_t expo;
+    uint32_t pad_;
 };
+constexpr uint32_t kExpoOne = 0x3FF00000u;
 inline PhiloxKeys make_philox_keys(uint64_t seed) {
     PhiloxKeys pk;
+    pk.expo = kExpoOne;
+    pk.pad_ = 0;
     uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
     for (int r = 0; r < 10; ++r) {
         pk.k0[r] = a;
@@ -135,9 +144,19 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
 // -- the fused kernels consume v directly and never form r: one fp64 instruction per dimension
 // less than r = fma(..), 1-r, 50*(..) (8 of the 152 fp64 instructions per event at d = 8), with
 // bit-identical xn.  Identical to oracle/vegas_oracle.c::u52_to_uniform / u32_to_uniform.
-__device__ __forceinline__ double u52_to_v(uint32_t hi, uint32_t lo) {
+// (word & 0xFFFFF) | expo in one LOP3 when expo is a register (LUT 0xEA = (a & b) | c)
+__device__ __forceinline__ uint32_t mantissa_hi(uint32_t word, uint32_t expo) {
+#ifndef VF_HOST_SHIM
+    uint32_t h;
+    asm("lop3.b32 %0, %1, 0xFFFFF, %2, 0xEA;" : "=r"(h) : "r"(word), "r"(expo));
+    return h;
+#else
+    return (word & 0xFFFFFu) | expo;
+#endif
+}
+__device__ __forceinline__ double u52_to_v(uint32_t hi, uint32_t lo, uint32_t expo = kExpoOne) {
     // two words, 52-bit mantissa fill (like tf.random.uniform for float64)
-    const double m = __hiloint2double((int)(0x3FF00000u | (hi & 0xFFFFFu)), (int)lo);
+    const double m = __hiloint2double((int)mantissa_hi(hi, expo), (int)lo);
     constexpr double S = 1.0 - 2.0 * kTechCut;
     constexpr double C = 3.0 * kTechCut;  // (1 + T) - S
     return fma(m, S, C);
@@ -165,9 +184,9 @@ struct Rng {
     static_assert(RB == 52 || RB == 32, "rng_bits is 52 or 32");
     static constexpr int kPerCall = RB == 32 ? 4 : 2;
     // v = 2 - r of uniform h of the block (see above)
-    static __device__ __forceinline__ double v(const uint4& o, int h) {
+    static __device__ __forceinline__ double v(const uint4& o, int h, uint32_t expo = kExpoOne) {
         if (RB == 32) return u32_to_v(h == 0 ? o.x : (h == 1 ? o.y : (h == 2 ? o.z : o.w)));
-        return h == 0 ? u52_to_v(o.x, o.y) : u52_to_v(o.z, o.w);
+        return h == 0 ? u52_to_v(o.x, o.y, expo) : u52_to_v(o.z, o.w, expo);
     }
     static __device__ __forceinline__ double uniform(const uint4& o, int h) {
         return __dsub_rn(2.0, v(o, h));
@@ -197,6 +216,72 @@ __device__ __forceinline__ void vegas_map_dim(double xn, const char* __restrict_
     x = __dadd_rn(e.x, __dmul_rn(e.y, aux));  // :76, mul then add
     wfac = __dmul_rn(e.y, kFBins);            // :78
 }
+
+#ifndef VF_EXP_FLOOR
+#define VF_EXP_FLOOR 0
+#endif
+#ifndef VF_EXP_PRMT
+#define VF_EXP_PRMT 0
+#endif
+#ifndef VF_HOST_SHIM
+// The fused kernels address shared memory with explicit 32-bit shared-window addresses: the row
+// address  bin*(TC*16) + (table base + lane slot)  is ONE integer multiply-add, the dimension
+// offset is the immediate of the LDS.128, and the histogram cell of the same bin is the row address
+// plus a per-lane constant when the two row pitches agree (TC*16 == HC*8).  (The pointer form
+// compiled to a shift, an OR and an add per dimension; the integer dispatch port is what the
+// event kernel is short of, profiles/r2_pipes2.txt.)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+template <int PITCH>
+__device__ __forceinline__ uint32_t row_addr(int bin, uint32_t base) {
+    uint32_t r;
+#if VF_EXP_PRMT == 2
+    r = base + (uint32_t)bin * (uint32_t)PITCH;  // experiment: let ptxas choose (LEA?)
+#elif VF_EXP_PRMT == 1
+    // experiment: PITCH == 256 and base < 256 (lane slot only; the table base rides in the
+    // uniform-register slot of the LDS): byte 1 of the address is the bin -- a byte permute on the
+    // ALU pipe instead of an integer multiply-add on the FMA-heavy pipe
+    static_assert(PITCH == 256, "byte-permute addressing needs 256-byte rows");
+    asm("prmt.b32 %0, %1, %2, 0x3240;" : "=r"(r) : "r"(base), "r"(bin));
+#else
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(bin), "n"(PITCH), "r"(base));
+#endif
+    return r;
+}
+// `off` is a compile-time constant after unrolling: ptxas folds it into the address immediate
+__device__ __forceinline__ double2 lds_f64x2(uint32_t addr, uint32_t off) {
+    double2 e;
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(e.x), "=d"(e.y) : "r"(addr + off));
+    return e;
+}
+__device__ __forceinline__ void red_shared_f64(uint32_t addr, uint32_t off, double v) {
+    asm volatile("red.shared.add.f64 [%0], %1;" ::"r"(addr + off), "d"(v) : "memory");
+}
+// vegas_map_dim on a shared-window address; `row` returns bin*(TC*16) + tbl_s for the histogram,
+// `off` is the byte offset of the dimension's table
+template <int TC>
+__device__ __forceinline__ void vegas_map_dim_s(double xn, uint32_t tbl_s, uint32_t off, double& x,
+                                                double& wfac, int& bin, uint32_t& row) {
+#if VF_EXP_FLOOR == 2   // experiment: truncation and back-conversion on the XU pipe
+    bin = __double2int_rz(xn);
+    const double fl = __int2double_rn(bin);
+#elif VF_EXP_FLOOR == 1  // experiment: bin from the round-down add, floor from an I2F
+    const double t = __dadd_rd(xn, kTwo52);
+    bin = __double2loint(t);
+    const double fl = __int2double_rn(bin);
+#else
+    const double t = __dadd_rd(xn, kTwo52);
+    bin = __double2loint(t);
+    const double fl = __dsub_rn(t, kTwo52);   // tf.math.floor(xn), vflow.py:75
+#endif
+    const double aux = __dsub_rn(xn, fl);     // :75
+    row = row_addr<TC * 16>(bin, tbl_s);
+    const double2 e = lds_f64x2(row, off);
+    x = __dadd_rn(e.x, __dmul_rn(e.y, aux));  // :76, mul then add
+    wfac = __dmul_rn(e.y, kFBins);            // :78
+}
+#endif
 
 // y / b with IEEE round-to-nearest in three fp64 operations, given rb = rn(1/b):
 // q0 = rn(y*rb) is within 1 ulp of y/b, r = y - b*q0 is exact in one FMA, and q0 + r*rb rounds

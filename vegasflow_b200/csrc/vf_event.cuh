@@ -121,19 +121,45 @@ __device__ __forceinline__ void write_partials(double sum, double sum2, const do
 }
 
 // Histogram update of one event: hist[j][bin_j][slot] += tmp2 for every dimension
-// (vflow.py:370-387, utils.py:40-43).  sm_100 has no native shared-memory fp64 add: atomicAdd
-// compiles to a load / DADD / ATOMS.CAST.SPIN loop per dimension.  That plain form measured 4 %
-// faster over the whole kernel than issuing the eight loads, adds and ATOMS.CAS.64 back to back
-// with a common retry path (round 1), and faster than conflict-avoiding variants -- half-warps
-// on disjoint dimensions, one dimension at a time, 32 copies (profiles/r2_k1_variants.txt):
-// ~5.7 CAS retries per warp-event happen either way and the cost is the instruction count.
+// (vflow.py:370-387, utils.py:40-43).  sm_100 has no native shared-memory fp64 add: the
+// reduction compiles to a load / DADD / ATOMS.CAST.SPIN loop per dimension.  That plain form
+// measured 4 % faster over the whole kernel than issuing the eight loads, adds and ATOMS.CAS.64
+// back to back with a common retry path (round 1), and faster than conflict-avoiding variants --
+// half-warps on disjoint dimensions, one dimension at a time, 32 copies
+// (profiles/r2_k1_variants.txt): ~5.7 CAS retries per warp-event happen either way and the cost
+// is the instruction count.
+// `row[j]` is the shared-window address of the event's TABLE row in dimension j when the table
+// and histogram row pitches agree (then the histogram cell is row + a per-lane constant, one
+// IADD3), else of its histogram row; the dimension offset folds into the address immediate.
+template <class C>
+struct HistAddr {
+    static constexpr bool kSamePitch = (C::TC * 16 == C::HC * 8);
+    uint32_t tbl_s, hist_s, delta;
+    uint32_t tbl_u;  // warp-uniform part of the table address (experiment VF_EXP_PRMT), else 0
+    __device__ __forceinline__ HistAddr(const void* tbl, const void* hist, int lane) {
+#if VF_EXP_PRMT == 1
+        tbl_u = smem_u32(tbl);
+        tbl_s = (uint32_t)(lane % C::TC) * 16u;
+        hist_s = smem_u32(hist) - tbl_u + (uint32_t)(lane % C::HC) * 8u;
+#else
+        tbl_u = 0;
+        tbl_s = smem_u32(tbl) + (uint32_t)(lane % C::TC) * 16u;
+        hist_s = smem_u32(hist) + (uint32_t)(lane % C::HC) * 8u;
+#endif
+        delta = hist_s - tbl_s;
+    }
+    // what to keep per dimension until the histogram update
+    __device__ __forceinline__ uint32_t keep(int bin, uint32_t tbl_row) const {
+        return kSamePitch ? tbl_row : row_addr<C::HC * 8>(bin, hist_s);
+    }
+};
 template <class C, int NDIM>
-__device__ __forceinline__ void hist_update(char* hist_lane, const int (&bin)[NDIM], double tmp2) {
+__device__ __forceinline__ void hist_update(const HistAddr<C>& ha, const uint32_t (&row)[NDIM],
+                                            double tmp2) {
 #pragma unroll
     for (int j = 0; j < NDIM; ++j)
-        atomicAdd(reinterpret_cast<double*>(hist_lane + j * (kBins * C::HC * 8) +
-                                            bin[j] * (C::HC * 8)),
-                  tmp2);
+        red_shared_f64(HistAddr<C>::kSamePitch ? row[j] + ha.delta : row[j],
+                       ha.tbl_u + (uint32_t)j * (kBins * C::HC * 8), tmp2);
 }
 
 // ---------------------------------------------------------------------------
@@ -160,14 +186,17 @@ event_kernel(const __grid_constant__ EventKernelArgs a) {
         pdl_wait();  // the previous tail kernel still reads the per-block records
     }
     const int lane = threadIdx.x & 31;
-    const char* tbl_lane = reinterpret_cast<const char*>(tbl) + (lane % C::TC) * 16;
-    char* hist_lane = reinterpret_cast<char*>(hist) + (lane % C::HC) * 8;
+    const HistAddr<C> ha(tbl, hist, lane);
     double sum = 0.0, sum2 = 0.0;
-    const uint64_t stride = (uint64_t)gridDim.x * C::kThreads;
-    for (uint64_t n = a.ev_begin + (uint64_t)blockIdx.x * C::kThreads + threadIdx.x; n < a.ev_end;
-         n += stride) {
+    // 32-bit trip count, 64-bit event index advanced by the launch-constant stride (a 64-bit
+    // compare and a re-derived stride per event cost six integer instructions)
+    const uint32_t stride = gridDim.x * C::kThreads;
+    uint64_t n = a.ev_begin + (uint64_t)blockIdx.x * C::kThreads + threadIdx.x;
+    const uint32_t trips = n < a.ev_end ? (uint32_t)((a.ev_end - n + stride - 1) / stride) : 0u;
+    const uint32_t expo = a.pk.expo;
+    for (uint32_t trip = 0; trip < trips; ++trip, n += stride) {
         double x[NDIM];
-        int bin[NDIM];
+        uint32_t row[NDIM];
         double w = 1.0;
         constexpr int PC = Rng<RB>::kPerCall;  // uniforms per Philox block
 #pragma unroll
@@ -178,13 +207,17 @@ event_kernel(const __grid_constant__ EventKernelArgs a) {
             for (int h = 0; h < PC; ++h) {
                 const int j = PC * p + h;
                 if (j < NDIM) {
-                    const double v = Rng<RB>::v(o, h);  // the uniform is r = 2 - v, exactly
+                    const double v = Rng<RB>::v(o, h, expo);  // the uniform is r = 2 - v, exactly
                     if (MODE == VF_MODE_VEGAS) {
                         // vflow.py:117: rn(50*(1-r)) with 1-r = v-1 exact == rn(50*v - 50)
                         const double xn = fma(v, kFBins, -kFBins);
                         double wfac;
-                        vegas_map_dim<C::TC>(xn, tbl_lane + j * (kBins * C::TC * 16), x[j], wfac,
-                                             bin[j]);
+                        int bin;
+                        uint32_t trow;
+                        vegas_map_dim_s<C::TC>(xn, ha.tbl_s,
+                                               ha.tbl_u + (uint32_t)j * (kBins * C::TC * 16),
+                                               x[j], wfac, bin, trow);
+                        row[j] = ha.keep(bin, trow);
                         w = (j == 0) ? wfac : __dmul_rn(w, wfac);  // reduce_prod, vflow.py:78
                     } else {
                         x[j] = __dsub_rn(2.0, v);  // r itself, monte_carlo.py:290-298
@@ -199,7 +232,7 @@ event_kernel(const __grid_constant__ EventKernelArgs a) {
         const double tmp2 = __dmul_rn(tmp, tmp);           // vflow.py:417
         sum += tmp;                                        // vflow.py:420
         sum2 += tmp2;                                      // vflow.py:421
-        if (do_hist) hist_update<C, NDIM>(hist_lane, bin, tmp2);
+        if (do_hist) hist_update<C, NDIM>(ha, row, tmp2);
     }
     write_partials<C, NDIM>(sum, sum2, hist, do_hist, a.partials);
 }
@@ -305,8 +338,8 @@ plus_event_kernel(const __grid_constant__ PlusKernelArgs a) {
     stage_grid<C>(a.divisions, tbl, hist, do_hist);  // waits for the previous tail kernel
     __syncthreads();
     const int lane = threadIdx.x & 31;
-    const char* tbl_lane = reinterpret_cast<const char*>(tbl) + (lane % C::TC) * 16;
-    char* hist_lane = reinterpret_cast<char*>(hist) + (lane % C::HC) * 8;
+    const HistAddr<C> ha(tbl, hist, lane);
+    const uint32_t expo = a.pk.expo;
     // the sample allocation lives on the device: after redistribute_samples the event count of
     // the next iteration is ev_offset[n_cubes] (vflowplus.py:163), never copied to the host
     const int64_t n_events = a.n_events >= 0 ? a.n_events : a.ev_offset[a.n_cubes];
@@ -374,6 +407,7 @@ plus_event_kernel(const __grid_constant__ PlusKernelArgs a) {
         }
         double x[NDIM];
         int bin[NDIM];
+        uint32_t row[NDIM];
         double w = 1.0;
         constexpr int PC = Rng<RB>::kPerCall;
 #pragma unroll
@@ -390,11 +424,14 @@ plus_event_kernel(const __grid_constant__ PlusKernelArgs a) {
                     // stream r = 2 - v exactly, and coords[] holds points + 2 (an exact small
                     // integer): rn(points + r) == rn((points + 2) - v)
                     const double pr = EXT ? __dadd_rn(coords[j], a.rnds[e * NDIM + j])
-                                          : __dsub_rn(coords[j], Rng<RB>::v(o, h));
+                                          : __dsub_rn(coords[j], Rng<RB>::v(o, h, expo));
                     const double xn = div_rn_by(__dmul_rn(pr, kFBins), fstrat, rstrat);
                     double wfac;
-                    vegas_map_dim<C::TC>(xn, tbl_lane + j * (kBins * C::TC * 16), x[j], wfac,
-                                         bin[j]);
+                    uint32_t trow;
+                    vegas_map_dim_s<C::TC>(xn, ha.tbl_s,
+                                           ha.tbl_u + (uint32_t)j * (kBins * C::TC * 16), x[j],
+                                           wfac, bin[j], trow);
+                    row[j] = ha.keep(bin[j], trow);
                     w = (j == 0) ? wfac : __dmul_rn(w, wfac);
                 }
             }
@@ -406,7 +443,7 @@ plus_event_kernel(const __grid_constant__ PlusKernelArgs a) {
         const double tmp2 = __dmul_rn(tmp, tmp);  // vflowplus.py:210
         s1 += tmp;
         s2 += tmp2;
-        if (do_hist) hist_update<C, NDIM>(hist_lane, bin, tmp2);
+        if (do_hist) hist_update<C, NDIM>(ha, row, tmp2);
         if (EXT) {
 #pragma unroll
             for (int j = 0; j < NDIM; ++j) {
