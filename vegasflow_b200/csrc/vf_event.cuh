@@ -41,6 +41,16 @@ struct CfgT {
 template <class I, int NDIM>
 using Cfg = CfgT<NDIM, I::kHeavy>;
 
+#ifndef VF_EXP_CLOCK
+#define VF_EXP_CLOCK 0
+#endif
+#ifndef VF_EXP_DYN
+#define VF_EXP_DYN 0
+#endif
+#if VF_EXP_CLOCK
+__device__ long long g_exp_clock[148 * 32 + 148];
+#endif
+
 struct EventKernelArgs {
     const double* divisions;  // [NDIM][51]
     double* partials;         // workspace: scalars[grid][2] | acc[NDIM*50]
@@ -188,13 +198,16 @@ event_kernel(const __grid_constant__ EventKernelArgs a) {
     const int lane = threadIdx.x & 31;
     const HistAddr<C> ha(tbl, hist, lane);
     double sum = 0.0, sum2 = 0.0;
+#if VF_EXP_CLOCK
+    const long long exp_t0 = clock64();
+#endif
     // 32-bit trip count, 64-bit event index advanced by the launch-constant stride (a 64-bit
     // compare and a re-derived stride per event cost six integer instructions)
     const uint32_t stride = gridDim.x * C::kThreads;
     uint64_t n = a.ev_begin + (uint64_t)blockIdx.x * C::kThreads + threadIdx.x;
     const uint32_t trips = n < a.ev_end ? (uint32_t)((a.ev_end - n + stride - 1) / stride) : 0u;
     const uint32_t expo = a.pk.expo;
-    for (uint32_t trip = 0; trip < trips; ++trip, n += stride) {
+    auto one_event = [&](const uint64_t n) {
         double x[NDIM];
         uint32_t row[NDIM];
         double w = 1.0;
@@ -233,8 +246,42 @@ event_kernel(const __grid_constant__ EventKernelArgs a) {
         sum += tmp;                                        // vflow.py:420
         sum2 += tmp2;                                      // vflow.py:421
         if (do_hist) hist_update<C, NDIM>(ha, row, tmp2);
+    };
+#if VF_EXP_DYN
+    // experiment: the block's warp-events (trip k, warp w) are handed out in chunks of VF_EXP_DYN
+    // from a shared counter, so that all warps leave the loop together
+    {
+        __shared__ uint32_t s_next;
+        if (threadIdx.x == 0) s_next = 0;
+        __syncthreads();
+        constexpr uint32_t kWarps = C::kThreads / 32;
+        const uint64_t n_blk = a.ev_begin + (uint64_t)blockIdx.x * C::kThreads;
+        const uint32_t trips_blk =
+            n_blk < a.ev_end ? (uint32_t)((a.ev_end - n_blk + stride - 1) / stride) : 0u;
+        const uint32_t total = trips_blk * kWarps;
+        for (;;) {
+            uint32_t c0 = 0;
+            if (lane == 0) c0 = atomicAdd(&s_next, (uint32_t)VF_EXP_DYN);
+            c0 = __shfl_sync(0xffffffffu, c0, 0);
+            if (c0 >= total) break;
+            const uint32_t c1 = min(c0 + (uint32_t)VF_EXP_DYN, total);
+#pragma unroll 1
+            for (uint32_t c = c0; c < c1; ++c) {
+                const uint64_t ne = n_blk + (uint64_t)(c / kWarps) * stride + (c % kWarps) * 32 + lane;
+                if (ne < a.ev_end) one_event(ne);
+            }
+        }
     }
+#else
+    for (uint32_t trip = 0; trip < trips; ++trip, n += stride) one_event(n);
+#endif
+#if VF_EXP_CLOCK  // experiment: when does each warp leave the event loop?
+    if (lane == 0) g_exp_clock[blockIdx.x * (C::kThreads / 32) + (threadIdx.x >> 5)] = clock64() - exp_t0;
+#endif
     write_partials<C, NDIM>(sum, sum2, hist, do_hist, a.partials);
+#if VF_EXP_CLOCK
+    if (threadIdx.x == 0) g_exp_clock[gridDim.x * (C::kThreads / 32) + blockIdx.x] = clock64() - exp_t0;
+#endif
 }
 
 // ---------------------------------------------------------------------------
