@@ -1,6 +1,7 @@
 // Experiment harness (not product code), round 2: times the PRODUCT event kernel
-// (vegasflow_b200/csrc/vf_event.cuh) standalone on 1e8 events; variants are selected with -DVF_EXP_*
-// switches that the product headers honour, one binary per variant:
+// (vegasflow_b200/csrc/vf_event.cuh) standalone on 1e8 events.  The -DVF_EXP_* switches that
+// selected the recorded variants (profiles/r2_k1_r3_*.txt) lived in the product headers up to commit
+// "Experiments on the product event kernel: per-warp loop-exit clocks ..." and were removed after:
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -fmad=false -std=c++17 -I include
 //        -I vegasflow_b200/csrc [-DVF_EXP_...] scripts/exp/k1_r3.cu -o scripts/exp/k1_r3_<variant>
 // Prints best-of-5 kernel time, events/s and checksums (sum wf, sum wf^2, sum of the histogram) so
@@ -62,22 +63,6 @@ int main(int argc, char** argv) {
     double s1 = 0, s2 = 0, sh = 0;
     for (int b = 0; b < blocks; ++b) { s1 += h[2 * b]; s2 += h[2 * b + 1]; }
     for (int i = 0; i < d * kBins; ++i) sh += h[ws_acc_offset() + i];
-#if VF_EXP_CLOCK
-    {
-        std::vector<long long> clk(148 * 32 + 148);
-        cudaMemcpyFromSymbol(clk.data(), g_exp_clock, clk.size() * 8);
-        // per scheduler (warp % 4): finish order of its 8 warps, averaged over the SMs
-        printf("# loop-exit clock of warp w relative to the block's end (fraction of the block's duration), mean over 148 blocks\n");
-        for (int w = 0; w < 32; ++w) {
-            double f = 0, fmin = 1e9, fmax = 0;
-            for (int b = 0; b < 148; ++b) {
-                const double r = (double)clk[b * 32 + w] / (double)clk[148 * 32 + b];
-                f += r; fmin = r < fmin ? r : fmin; fmax = r > fmax ? r : fmax;
-            }
-            printf("warp %2d (sched %d): mean %.4f  min %.4f  max %.4f\n", w, w % 4, f / 148, fmin, fmax);
-        }
-    }
-#endif
     cudaFuncAttributes fa; cudaFuncGetAttributes(&fa, kern);
     printf("%-44s d=%d regs=%3d smem=%6zu  %8.4f ms  %.4e ev/s  sum=%.15g sum2=%.15g hist=%.15g %s\n", EXP_NAME, d,
            fa.numRegs, (size_t)C::kSmemBytes, best, n / (best * 1e-3), s1, s2, sh,

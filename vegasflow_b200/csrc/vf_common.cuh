@@ -217,12 +217,6 @@ __device__ __forceinline__ void vegas_map_dim(double xn, const char* __restrict_
     wfac = __dmul_rn(e.y, kFBins);            // :78
 }
 
-#ifndef VF_EXP_FLOOR
-#define VF_EXP_FLOOR 0
-#endif
-#ifndef VF_EXP_PRMT
-#define VF_EXP_PRMT 0
-#endif
 #ifndef VF_HOST_SHIM
 // The fused kernels address shared memory with explicit 32-bit shared-window addresses: the row
 // address  bin*(TC*16) + (table base + lane slot)  is ONE integer multiply-add, the dimension
@@ -236,17 +230,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 template <int PITCH>
 __device__ __forceinline__ uint32_t row_addr(int bin, uint32_t base) {
     uint32_t r;
-#if VF_EXP_PRMT == 2
-    r = base + (uint32_t)bin * (uint32_t)PITCH;  // experiment: let ptxas choose (LEA?)
-#elif VF_EXP_PRMT == 1
-    // experiment: PITCH == 256 and base < 256 (lane slot only; the table base rides in the
-    // uniform-register slot of the LDS): byte 1 of the address is the bin -- a byte permute on the
-    // ALU pipe instead of an integer multiply-add on the FMA-heavy pipe
-    static_assert(PITCH == 256, "byte-permute addressing needs 256-byte rows");
-    asm("prmt.b32 %0, %1, %2, 0x3240;" : "=r"(r) : "r"(base), "r"(bin));
-#else
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(bin), "n"(PITCH), "r"(base));
-#endif
     return r;
 }
 // `off` is a compile-time constant after unrolling: ptxas folds it into the address immediate
@@ -263,18 +247,12 @@ __device__ __forceinline__ void red_shared_f64(uint32_t addr, uint32_t off, doub
 template <int TC>
 __device__ __forceinline__ void vegas_map_dim_s(double xn, uint32_t tbl_s, uint32_t off, double& x,
                                                 double& wfac, int& bin, uint32_t& row) {
-#if VF_EXP_FLOOR == 2   // experiment: truncation and back-conversion on the XU pipe
-    bin = __double2int_rz(xn);
-    const double fl = __int2double_rn(bin);
-#elif VF_EXP_FLOOR == 1  // experiment: bin from the round-down add, floor from an I2F
-    const double t = __dadd_rd(xn, kTwo52);
-    bin = __double2loint(t);
-    const double fl = __int2double_rn(bin);
-#else
+    // floor via round-down add of 2^52 (see vegas_map_dim).  Taking the floor or the truncation
+    // through I2F / F2I on the XU pipe instead saves fp64 instructions but not time
+    // (profiles/r2_k1_r3_floor_exp_variants.txt).
     const double t = __dadd_rd(xn, kTwo52);
     bin = __double2loint(t);
     const double fl = __dsub_rn(t, kTwo52);   // tf.math.floor(xn), vflow.py:75
-#endif
     const double aux = __dsub_rn(xn, fl);     // :75
     row = row_addr<TC * 16>(bin, tbl_s);
     const double2 e = lds_f64x2(row, off);

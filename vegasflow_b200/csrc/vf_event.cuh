@@ -41,16 +41,6 @@ struct CfgT {
 template <class I, int NDIM>
 using Cfg = CfgT<NDIM, I::kHeavy>;
 
-#ifndef VF_EXP_CLOCK
-#define VF_EXP_CLOCK 0
-#endif
-#ifndef VF_EXP_DYN
-#define VF_EXP_DYN 0
-#endif
-#if VF_EXP_CLOCK
-__device__ long long g_exp_clock[148 * 32 + 148];
-#endif
-
 struct EventKernelArgs {
     const double* divisions;  // [NDIM][51]
     double* partials;         // workspace: scalars[grid][2] | acc[NDIM*50]
@@ -145,17 +135,9 @@ template <class C>
 struct HistAddr {
     static constexpr bool kSamePitch = (C::TC * 16 == C::HC * 8);
     uint32_t tbl_s, hist_s, delta;
-    uint32_t tbl_u;  // warp-uniform part of the table address (experiment VF_EXP_PRMT), else 0
     __device__ __forceinline__ HistAddr(const void* tbl, const void* hist, int lane) {
-#if VF_EXP_PRMT == 1
-        tbl_u = smem_u32(tbl);
-        tbl_s = (uint32_t)(lane % C::TC) * 16u;
-        hist_s = smem_u32(hist) - tbl_u + (uint32_t)(lane % C::HC) * 8u;
-#else
-        tbl_u = 0;
         tbl_s = smem_u32(tbl) + (uint32_t)(lane % C::TC) * 16u;
         hist_s = smem_u32(hist) + (uint32_t)(lane % C::HC) * 8u;
-#endif
         delta = hist_s - tbl_s;
     }
     // what to keep per dimension until the histogram update
@@ -169,7 +151,7 @@ __device__ __forceinline__ void hist_update(const HistAddr<C>& ha, const uint32_
 #pragma unroll
     for (int j = 0; j < NDIM; ++j)
         red_shared_f64(HistAddr<C>::kSamePitch ? row[j] + ha.delta : row[j],
-                       ha.tbl_u + (uint32_t)j * (kBins * C::HC * 8), tmp2);
+                       (uint32_t)j * (kBins * C::HC * 8), tmp2);
 }
 
 // ---------------------------------------------------------------------------
@@ -198,9 +180,6 @@ event_kernel(const __grid_constant__ EventKernelArgs a) {
     const int lane = threadIdx.x & 31;
     const HistAddr<C> ha(tbl, hist, lane);
     double sum = 0.0, sum2 = 0.0;
-#if VF_EXP_CLOCK
-    const long long exp_t0 = clock64();
-#endif
     // 32-bit trip count, 64-bit event index advanced by the launch-constant stride (a 64-bit
     // compare and a re-derived stride per event cost six integer instructions)
     const uint32_t stride = gridDim.x * C::kThreads;
@@ -228,7 +207,7 @@ event_kernel(const __grid_constant__ EventKernelArgs a) {
                         int bin;
                         uint32_t trow;
                         vegas_map_dim_s<C::TC>(xn, ha.tbl_s,
-                                               ha.tbl_u + (uint32_t)j * (kBins * C::TC * 16),
+                                               (uint32_t)j * (kBins * C::TC * 16),
                                                x[j], wfac, bin, trow);
                         row[j] = ha.keep(bin, trow);
                         w = (j == 0) ? wfac : __dmul_rn(w, wfac);  // reduce_prod, vflow.py:78
@@ -247,41 +226,12 @@ event_kernel(const __grid_constant__ EventKernelArgs a) {
         sum2 += tmp2;                                      // vflow.py:421
         if (do_hist) hist_update<C, NDIM>(ha, row, tmp2);
     };
-#if VF_EXP_DYN
-    // experiment: the block's warp-events (trip k, warp w) are handed out in chunks of VF_EXP_DYN
-    // from a shared counter, so that all warps leave the loop together
-    {
-        __shared__ uint32_t s_next;
-        if (threadIdx.x == 0) s_next = 0;
-        __syncthreads();
-        constexpr uint32_t kWarps = C::kThreads / 32;
-        const uint64_t n_blk = a.ev_begin + (uint64_t)blockIdx.x * C::kThreads;
-        const uint32_t trips_blk =
-            n_blk < a.ev_end ? (uint32_t)((a.ev_end - n_blk + stride - 1) / stride) : 0u;
-        const uint32_t total = trips_blk * kWarps;
-        for (;;) {
-            uint32_t c0 = 0;
-            if (lane == 0) c0 = atomicAdd(&s_next, (uint32_t)VF_EXP_DYN);
-            c0 = __shfl_sync(0xffffffffu, c0, 0);
-            if (c0 >= total) break;
-            const uint32_t c1 = min(c0 + (uint32_t)VF_EXP_DYN, total);
-#pragma unroll 1
-            for (uint32_t c = c0; c < c1; ++c) {
-                const uint64_t ne = n_blk + (uint64_t)(c / kWarps) * stride + (c % kWarps) * 32 + lane;
-                if (ne < a.ev_end) one_event(ne);
-            }
-        }
-    }
-#else
+    // Static striding.  The warps of a block leave this loop over the last 11 % of its duration
+    // (the scheduler favours high warp ids), but handing the events out dynamically so that they
+    // leave together is 1-2 % SLOWER: the kernel is bound by pipe throughput, not by the number
+    // of resident warps (profiles/r2_k1_r3_tail_dynamic_variants.txt).
     for (uint32_t trip = 0; trip < trips; ++trip, n += stride) one_event(n);
-#endif
-#if VF_EXP_CLOCK  // experiment: when does each warp leave the event loop?
-    if (lane == 0) g_exp_clock[blockIdx.x * (C::kThreads / 32) + (threadIdx.x >> 5)] = clock64() - exp_t0;
-#endif
     write_partials<C, NDIM>(sum, sum2, hist, do_hist, a.partials);
-#if VF_EXP_CLOCK
-    if (threadIdx.x == 0) g_exp_clock[gridDim.x * (C::kThreads / 32) + blockIdx.x] = clock64() - exp_t0;
-#endif
 }
 
 // ---------------------------------------------------------------------------
@@ -476,7 +426,7 @@ plus_event_kernel(const __grid_constant__ PlusKernelArgs a) {
                     double wfac;
                     uint32_t trow;
                     vegas_map_dim_s<C::TC>(xn, ha.tbl_s,
-                                           ha.tbl_u + (uint32_t)j * (kBins * C::TC * 16), x[j],
+                                           (uint32_t)j * (kBins * C::TC * 16), x[j],
                                            wfac, bin[j], trow);
                     row[j] = ha.keep(bin[j], trow);
                     w = (j == 0) ? wfac : __dmul_rn(w, wfac);

@@ -38,53 +38,6 @@ static __constant__ double kExpCoef[12] = {
     2.4801521322368692e-05, 2.7557268480310024e-06, 2.7620075879983367e-07,
     2.5100375832561234e-08};
 
-#ifndef VF_EXP_EXPTAB
-#define VF_EXP_EXPTAB 0
-#endif
-#if VF_EXP_EXPTAB
-// experiment: x = (64k + j) ln2/64 + r, |r| <= ln2/128; exp(x) = 2^k * T[j] * (1 + expm1(r)),
-// expm1(r) = r + r^2 (1/2 + r/6 + r^2/24 + r^3/120) (truncation 3.5e-17): 10 fp64 instructions
-// instead of 15, one table load
-static __device__ const double kExp2Tab[64] = {
-    1.0, 1.0108892860517005, 1.0218971486541166, 1.0330248790212284,
-    1.0442737824274138, 1.0556451783605572, 1.0671404006768237, 1.0787607977571199,
-    1.0905077326652577, 1.102382583307841, 1.1143867425958924, 1.1265216186082418,
-    1.1387886347566916, 1.1511892299529827, 1.1637248587775775, 1.1763969916502812,
-    1.189207115002721, 1.202156731452703, 1.215247359980469, 1.22848053610687,
-    1.241857812073484, 1.255380757024691, 1.2690509571917332, 1.2828700160787783,
-    1.2968395546510096, 1.3109612115247644, 1.3252366431597413, 1.339667524053303,
-    1.3542555469368927, 1.3690024229745905, 1.383909881963832, 1.3989796725383112,
-    1.4142135623730951, 1.42961333839197, 1.4451808069770467, 1.460917794180647,
-    1.4768261459394993, 1.4929077282912648, 1.5091644275934228, 1.5255981507445384,
-    1.5422108254079407, 1.559004400237837, 1.5759808451078865, 1.593142151342267,
-    1.6104903319492543, 1.6280274218573478, 1.645755478153965, 1.6636765803267364,
-    1.681792830507429, 1.7001063537185235, 1.718619298122478, 1.7373338352737062,
-    1.7562521603732995, 1.7753764925265212, 1.7947090750031072, 1.8142521755003989,
-    1.8340080864093424, 1.8539791250833855, 1.8741676341103, 1.8945759815869656,
-    1.9152065613971474, 1.9360617934922943, 1.9571441241754002, 1.978456026387951};
-__device__ __forceinline__ double exp_nonpositive(double x) {
-    const double kMagic = 6755399441055744.0;  // 1.5 * 2^52
-    const double t = fma(x, 92.33248261689366, kMagic);   // 64/ln2
-    const int n = __double2loint(t);
-    const double nf = t - kMagic;
-    double r = fma(nf, -0.010830424696249145, x);         // ln2/64, high part
-    r = fma(nf, -3.623510646634843e-19, r);               // low part
-    const double T = __ldg(&kExp2Tab[n & 63]);
-    const int k = n >> 6;
-    const double r2 = r * r;
-    double P = fma(8.3333333333333332e-3, r, 4.1666666666666664e-2);
-    P = fma(P, r, 1.6666666666666666e-1);
-    P = fma(P, r, 0.5);
-    const double q = fma(P, r2, r);
-    const double p = fma(T, q, T);
-    if ((uint32_t)__double2hiint(x) > 0xC085E000u) {
-        if (x < -800.0) return 0.0;
-        const double s = __hiloint2double(__double2hiint(p) + ((k + 256) << 20), __double2loint(p));
-        return s * 8.636168555094445e-78;  // 2^-256
-    }
-    return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
-}
-#else
 __device__ __forceinline__ double exp_nonpositive(double x) {
     const double kMagic = 6755399441055744.0;  // 1.5 * 2^52: round-to-nearest-integer add
     const double t = fma(x, 1.4426950408889634, kMagic);
@@ -105,7 +58,6 @@ __device__ __forceinline__ double exp_nonpositive(double x) {
     }
     return __hiloint2double(__double2hiint(p) + (k << 20), __double2loint(p));
 }
-#endif
 
 struct SymGauss {
     static constexpr int kFixedDim = 0;
