@@ -841,16 +841,41 @@ __device__ void plus_cube_block(const PlusTailArgs& a, const Xchg& xc) {
     if (a.zero_sums)
         for (int64_t c = c0; c < c1; ++c) a.ress[c] = a.ress2[c] = 0.0;
     const bool redistribute = a.adaptive && !failed;
+    // the damped variances are needed twice (their sum, then per cube): pow() is the bulk of this
+    // block's time, so a thread keeps those of its slice in registers when the slice is short
+    // (n_cubes <= 10240 covers the reference's cap of 10^4 cubes, vflowplus.py:121-124)
+    constexpr int kKeep = 10;
+    const bool keep = per <= kKeep;
+    double dv[kKeep];
     double damp = 0.0;
-    if (redistribute)
-        for (int64_t c = c0; c < c1; ++c)
-            damp += pow(fmax(a.arr_var[c], 0.0), kBeta / 2);  // :157 (clamped, documented)
+    if (redistribute) {
+        if (keep) {
+#pragma unroll
+            for (int k = 0; k < kKeep; ++k) {
+                dv[k] = 0.0;
+                if (c0 + k < c1) {
+                    dv[k] = pow(fmax(a.arr_var[c0 + k], 0.0), kBeta / 2);  // :157 (clamped)
+                    damp += dv[k];
+                }
+            }
+        } else {
+            for (int64_t c = c0; c < c1; ++c)
+                damp += pow(fmax(a.arr_var[c], 0.0), kBeta / 2);  // :157 (clamped, documented)
+        }
+    }
     const double dsum = redistribute ? block_sum_1024(damp, scratch) : 0.0;
     long long local = 0;
     for (int64_t c = c0; c < c1; ++c) {
         int32_t nv = a.n_ev[c];
         if (redistribute && dsum > 0.0) {
-            const double d = pow(fmax(a.arr_var[c], 0.0), kBeta / 2);
+            double d = 0.0;
+            if (keep) {
+#pragma unroll
+                for (int k = 0; k < kKeep; ++k)
+                    if (c - c0 == k) d = dv[k];
+            } else {
+                d = pow(fmax(a.arr_var[c], 0.0), kBeta / 2);
+            }
             const double want =
                 __ddiv_rn(__ddiv_rn(__dmul_rn(d, a.init_calls), 2.0), dsum);  // :160
             nv = (int32_t)fmax((double)a.min_neval, want);                    // :158-162
