@@ -106,7 +106,8 @@ __device__ __forceinline__ cplx cmul(cplx a, cplx b) {
 __device__ __forceinline__ cplx cadd(cplx a, cplx b) { return {a.re + b.re, a.im + b.im}; }
 __device__ __forceinline__ cplx cscale(cplx a, double r) { return {a.re * r, a.im * r}; }  // a*complex(r,0)
 __device__ __forceinline__ cplx cneg(cplx a) { return {-a.re, -a.im}; }
-__device__ __forceinline__ double cabs(cplx a) { return hypot(a.re, a.im); }
+// |a| without hypot's scaling: the amplitudes are far from the overflow/underflow thresholds
+__device__ __forceinline__ double cabs(cplx a) { return sqrt(a.re * a.re + a.im * a.im); }
 
 struct Mom {
     double e, x, y, z;
@@ -134,30 +135,75 @@ __device__ __forceinline__ double clip1(double v) {
     return r;
 }
 
-// theta/phi of drellyan u0 (:93-115) and of ubar0 in both examples
-// (drellyan :140-162, singletop :156-178).
-__device__ __forceinline__ Angles angles_acos(const Mom& p) {
-    const double rz = p.z / p.e;
-    double theta, phi;
-    if (p.x == 0.0) {
-        theta = rz;                    // theta1
-        if (rz > 0.0) theta = 0.0;
-        if (rz < 0.0) theta = M_PI;
-        phi = 0.0;
-    } else {
-        theta = acos(clip1(rz));
-        const double rx = p.x / p.e / sin(theta);
-        phi = acos(clip1(rx));
-        const double ry = p.y / p.e;
-        if (ry < 0.0) phi = -phi;
+// The reference takes theta = acos(pz/E), phi = +-acos(px/E/sin(theta)) and then needs only
+// cos(theta/2), sin(theta/2), cos(phi), sin(phi) (drellyan :93-162, singletop :105-178).  With
+// c = clip(pz/E) and cx = clip(px/E/sin(theta)) these are, for the SAME c and cx,
+//     cos(theta/2) = sqrt((1+c)/2)   sin(theta/2) = sqrt((1-c)/2)   sin(theta) = 2 sin cos (theta/2)
+//     cos(phi) = cx                  sin(phi) = +-sqrt((1-cx)(1+cx))
+// i.e. four square roots instead of two acos, one sin and two sincos per momentum -- accurate
+// evaluations of the same functions of the same arguments (1-c, 1-cx are exact near the ends
+// where the acos route is accurate as well), so both stay inside the 1e-12 parity bar
+// (tests/test_device_source_on_host.py, tests/test_parity_gpu.py).  The p.x == 0 branch keeps
+// the reference's numerically evaluated constants: cos(pi/2) = 6.123e-17, sin(pi) = 1.2246e-16.
+constexpr double kCosHalfPi = 6.123233995736766e-17;   // np.cos(np.pi / 2)
+constexpr double kSinPi = 1.2246467991473532e-16;      // np.sin(np.pi)
+
+// (cos, sin)(theta/2) for the beam-axis case px == 0: theta in {0, pi, rz (0 or NaN)}
+__device__ __forceinline__ void half_angle_axis(double rz, double& ch, double& sh) {
+    ch = 1.0;
+    sh = 0.0;
+    if (rz < 0.0) {
+        ch = kCosHalfPi;
+        sh = 1.0;
     }
+    if (rz != rz) ch = sh = rz;  // NaN passes through like sincos(NaN)
+}
+
+// theta/phi of drellyan u0 (:93-115) and ubar0 (:140-162) through the half-angle forms.
+__device__ __forceinline__ Angles angles_half(const Mom& p) {
+    const double rz = p.z / p.e;
     Angles a;
-    sincos(theta / 2, &a.sh, &a.ch);  // one argument reduction for both
-    if (phi == 0.0) {                 // beam-axis momenta (and phi2 == 0): cos 0 = 1, sin 0 = 0
-        a.cp = 1.0;
+    if (p.x == 0.0) {
+        half_angle_axis(rz, a.ch, a.sh);
+        a.cp = 1.0;  // phi = 0
         a.sp = 0.0;
     } else {
-        sincos(phi, &a.sp, &a.cp);
+        const double c = clip1(rz);
+        a.ch = sqrt(0.5 * (1.0 + c));
+        a.sh = sqrt(0.5 * (1.0 - c));
+        const double sin_theta = 2.0 * (a.sh * a.ch);
+        const double cx = clip1(p.x / p.e / sin_theta);
+        a.cp = cx;
+        a.sp = sqrt((1.0 - cx) * (1.0 + cx));
+        if (cx == -1.0) a.sp = kSinPi;  // phi == pi: the reference's sin(np.pi)
+        if (p.y / p.e < 0.0) a.sp = -a.sp;
+        if (cx == 1.0) a.sp = 0.0;  // phi == 0 (also -0): cos 0 = 1, sin 0 = 0
+    }
+    a.pref = spinor_prefact(p.e);
+    return a;
+}
+
+// The literal route (acos, sin, sincos) for single-top's ubar0 (singletop :156-178).  Single-top
+// keeps it: near threshold the projected top momentum is anti-parallel to the beam, theta -> pi,
+// and the reference's cos(theta/2) carries the rounding of theta = acos(.) as a RELATIVE error of
+// 2e-16 / cos(theta/2) that reaches 1e-8 -- amplitudes proportional to it agree with the
+// reference to 1e-12 only if theta is rounded the same way (0.4 % of uniformly drawn events would
+// miss the bar with the more accurate half-angle forms).  Drell-Yan has no such region.
+__device__ __forceinline__ Angles angles_acos(const Mom& p) {
+    const double rz = p.z / p.e;
+    Angles a;
+    a.cp = 1.0;  // phi == 0 (beam-axis momenta, and phi2 == 0): cos 0 = 1, sin 0 = 0
+    a.sp = 0.0;
+    if (p.x == 0.0) {
+        half_angle_axis(rz, a.ch, a.sh);  // theta1 in {0, pi}: sincos(theta/2) are constants
+    } else {
+        const double theta = acos(clip1(rz));
+        const double rx = p.x / p.e / sin(theta);
+        double phi = acos(clip1(rx));
+        const double ry = p.y / p.e;
+        if (ry < 0.0) phi = -phi;
+        sincos(theta / 2, &a.sh, &a.ch);  // one argument reduction for both
+        if (phi != 0.0) sincos(phi, &a.sp, &a.cp);
     }
     a.pref = spinor_prefact(p.e);
     return a;
@@ -166,24 +212,18 @@ __device__ __forceinline__ Angles angles_acos(const Mom& p) {
 // theta/phi of singletop u0 (:110-129): phi in {0, pi} from the sign of px/E.
 __device__ __forceinline__ Angles angles_st_u0(const Mom& p) {
     const double rz = p.z / p.e;
-    double theta, phi;
-    if (p.x == 0.0) {
-        theta = rz;
-        if (rz > 0.0) theta = 0.0;
-        if (rz < 0.0) theta = M_PI;
-        phi = 0.0;
-    } else {
-        theta = acos(clip1(rz));
-        const double rx = p.x / p.e;
-        phi = (rx < 0.0) ? M_PI : 0.0;
-    }
     Angles a;
-    sincos(theta / 2, &a.sh, &a.ch);  // one argument reduction for both
-    if (phi == 0.0) {                 // beam-axis momenta (and phi2 == 0): cos 0 = 1, sin 0 = 0
-        a.cp = 1.0;
-        a.sp = 0.0;
+    a.cp = 1.0;
+    a.sp = 0.0;
+    if (p.x == 0.0) {
+        half_angle_axis(rz, a.ch, a.sh);
     } else {
-        sincos(phi, &a.sp, &a.cp);
+        const double theta = acos(clip1(rz));
+        sincos(theta / 2, &a.sh, &a.ch);
+        if (p.x / p.e < 0.0) {  // phi = pi: the reference's np.cos(np.pi), np.sin(np.pi)
+            a.cp = -1.0;
+            a.sp = kSinPi;
+        }
     }
     a.pref = spinor_prefact(p.e);
     return a;
@@ -238,28 +278,30 @@ struct DrellYanLO {
         const double ecmo2 = mV / 2;
         const Mom p0{ecmo2, 0.0, 0.0, ecmo2};
         const Mom p1{ecmo2, 0.0, 0.0, -ecmo2};
-        const Mom pV{p0.e + p1.e, p0.x + p1.x, p0.y + p1.y, p0.z + p1.z};
-        const double YV = 0.5 * log(fabs((pV.e + pV.z) / (pV.e - pV.z)));
-        const double pVt2 = pV.x * pV.x + pV.y * pV.y;
+        // pV = p0 + p1 = (2 ecmo2, 0, 0, 0) with EXACT zeros, so YV = log(|1|)/2 = 0, pVt2 = 0 and
+        // pV.x cos + pV.y sin = 0 exactly (:53-59, dropped like the exact-zero spinor components).
+        const Mom pV{p0.e + p1.e, 0.0, 0.0, 0.0};
         const double phi = (2.0 * M_PI) * xa[3];  // :60, 2*np.pi*x3
         double sphi, cphi;
         sincos(phi, &sphi, &cphi);
-        const double root = sqrt(mV2 + pVt2);
-        const double ptmax = 0.5 * mV2 / (root - (pV.x * cphi + pV.y * sphi));
+        const double root = sqrt(mV2);
+        const double ptmax = 0.5 * mV2 / root;
         const double pta = ptmax * xa[2];
         const double ptx = pta * cphi, pty = pta * sphi;
-        const double Delta = (mV2 + 2 * (pV.x * ptx + pV.y * pty)) / 2.0 / pta / root;
-        const double yy = YV - acosh(Delta);
-        const double kallenF = 2.0 * ptmax / root / fabs(sinh(YV - yy));
-        const Mom p2{pta * cosh(yy), ptx, pty, pta * sinh(yy)};
+        const double Delta = mV2 / 2.0 / pta / root;
+        // yy = YV - acosh(Delta) = -acosh(Delta) (:64): cosh(yy) = Delta and
+        // sinh(yy) = -sqrt((Delta-1)(Delta+1)), with Delta - 1 exact (Delta = 1/x2 > 1)
+        const double shy = sqrt((Delta - 1.0) * (Delta + 1.0));
+        const double kallenF = 2.0 * ptmax / root / shy;
+        const Mom p2{pta * Delta, ptx, pty, -(pta * shy)};
         const Mom p3{pV.e - p2.e, pV.x - p2.x, pV.y - p2.y, pV.z - p2.z};
         double psw = (1.0 / (8.0 * M_PI)) * kallenF;  // :71, 1/(8*np.pi) folded in IEEE
         psw = psw * jac;
         const double flux = 1 / (2 * mV2);
         // qqxllx(-p1, -p0, p2, p3) :207-224
         const Mom q0 = mneg(p1), q1 = mneg(p0);
-        const Angles a0 = angles_acos(q0), a1 = angles_acos(q1), a2 = angles_acos(p2),
-                     a3 = angles_acos(p3);
+        const Angles a0 = angles_half(q0), a1 = angles_half(q1), a2 = angles_half(p2),
+                     a3 = angles_half(p3);
         // za(a,b) = ubar0(a,-1).u0(b,+1); zb(a,b) = ubar0(a,+1).u0(b,-1)
         const Spin2 ubm0 = ubar0_minus(a0);
         const cplx za01 = sdot(ubm0, u0_plus(a1));
