@@ -196,7 +196,11 @@ int vf_digest_from_uniforms(int mode, int integrand, int n_dim, int64_t n,
                             double* w /*[dev] [n]*/, int32_t* ind /*[dev] [n][n_dim]*/,
                             double* wf /*[dev] [n]*/, void* stream);
 
-/* The engine's uniforms for events [ev_begin, ev_begin+n): rnds [n][n_dim]; rng_bits 52 | 32. */
+/* The engine's uniforms for events [ev_begin, ev_begin+n): rnds [n][n_dim]; rng_bits 52 | 32.
+ * Stream definition (52): Philox4x32-10, key = seed, counter = (event_lo, event_hi, dim/2,
+ * iteration); words (2h, 2h+1) of the block fill the mantissa of m in [1,2); v = fma(m, 1-2T, 3T)
+ * with T = TECH_CUT; r = 2 - v, exact, a multiple of 2^-52 in (T, 1-T].  The fused kernels
+ * consume v directly (xn = fma(v, 50, -50) == 50*(1-r) bit for bit). */
 int vf_uniforms(int n_dim, uint64_t ev_begin, int64_t n, uint64_t seed, uint32_t iteration,
                 int rng_bits, double* rnds /*[dev]*/, void* stream);
 
