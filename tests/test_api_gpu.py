@@ -485,3 +485,55 @@ def test_user_cuda_integrand_runs_fused():
     f = (1.0 / 0.1 / np.sqrt(np.pi)) ** d * np.exp(-(((x - 0.5) / 0.1) ** 2).sum(axis=1))
     want = w / 5000 * f
     assert (np.abs(wf.cpu().numpy() - want) / want).max() < 1e-12
+
+
+@pytest.mark.gpu
+def test_integration_md_binding_declarations_drive_the_abi():
+    """INTEGRATION.md 1(b) sketches the reference-side ctypes binding.  The reference and a GPU
+    never share a machine here, so the sketch cannot run as written -- but its ctypes declarations
+    and its call sequences can: they are taken verbatim from the document, pointed at the built
+    library, and one VEGAS iteration loop driven through them (vf_run_event -> sigma ->
+    vf_refine_grid, exactly the calls of the sketch's `_run_event` / `refine_grid`) must give what
+    the shipped host layer gives for the same seed."""
+    import ctypes as C
+    import os
+    import re
+
+    from vegasflow_b200 import _lib as L
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    block = re.search(r"```python\n# src/vegasflow/b200.py.*?```", doc, re.S).group(0)
+    decl = re.search(r"(_lib\.vf_run_event\.restype.*?)\ndef _check", block, re.S).group(1)
+    lib = C.CDLL(L.SO_PATH)  # a fresh handle: only the document's declarations apply to it
+    exec(decl, {"C": C, "_lib": lib})
+    assert "_lib.vf_run_event(1, self._iid, d, 0, n, 1.0 / self.n_events, self._seed, self._it," in block
+    assert "_lib.vf_refine_grid(self.n_dim, self._packed.data_ptr(), self._grid.data_ptr(), None)" in block
+
+    d, n, n_iter, seed = 4, 200000, 3, 4242
+    iid = lib.vf_integrand_id(b"symgauss")
+    assert iid >= 0
+    ws = torch.zeros(lib.vf_workspace_bytes(d) // 8, dtype=torch.float64, device="cuda")
+    packed = torch.zeros(d * 50 + 2, dtype=torch.float64, device="cuda")
+    grid = torch.as_tensor(R.initial_divisions(d), device="cuda").contiguous()
+    got = []
+    for it in range(n_iter):  # the sketch's _run_event + refine_grid, argument for argument
+        rc = lib.vf_run_event(1, iid, d, 0, n, 1.0 / n, seed, it, 1, grid.data_ptr(), None, None,
+                              packed[d * 50:].data_ptr(), packed.data_ptr(), 0, ws.data_ptr(),
+                              ws.numel() * 8, None)
+        assert rc == 0, lib.vf_last_error().decode()
+        torch.cuda.synchronize()
+        res, res2 = packed[d * 50].item(), packed[d * 50 + 1].item()
+        got.append((res, float(R.vegas_sigma(res, res2, n))))
+        assert lib.vf_refine_grid(d, packed.data_ptr(), grid.data_ptr(), None) == 0
+    torch.cuda.synchronize()
+
+    inst = VegasFlow(d, n, verbose=False)
+    inst.set_seed(seed)
+    inst.compile(vf.integrands.symgauss)
+    inst.run_integration(n_iter)
+    want = [(h[0], h[1]) for h in inst.history[-n_iter:]] if hasattr(inst, "history") else None
+    if want:
+        for (r, s), (wr, ws_) in zip(got, want):
+            assert abs(r - float(wr)) <= 1e-9 * abs(r) and abs(s - float(ws_)) <= 1e-7 * s
+    np.testing.assert_allclose(grid.cpu().numpy(), inst.divisions.cpu().numpy(), rtol=0, atol=1e-10)
