@@ -28,11 +28,14 @@ using namespace vf;
 #ifndef EXP_NAME
 #define EXP_NAME "product kernel"
 #endif
+#ifndef EXP_INTEGRAND
+#define EXP_INTEGRAND SymGauss
+#endif
 
 int main(int argc, char** argv) {
     constexpr int d = EXP_DIM;
     const int64_t n = argc > 1 ? atoll(argv[1]) : 100000000;
-    using C = Cfg<SymGauss, d>;
+    using C = Cfg<EXP_INTEGRAND, d>;
     std::vector<double> div(d * kEdges);
     for (int j = 0; j < d; ++j) for (int b = 0; b <= kBins; ++b) {
         // a peaked grid like a trained symgauss one: bins concentrated around 1/2
@@ -44,7 +47,7 @@ int main(int argc, char** argv) {
     a.divisions = ddiv; a.partials = ws; a.ev_begin = 0; a.ev_end = (uint64_t)n; a.xjac = 1.0 / n; a.iteration = 1;
     a.train = 1; a.pk = make_philox_keys(2024);
     a.ic.p[0] = pow(1.0 / 0.1 / sqrt(M_PI), (double)d); a.ic.p[1] = (100.0 * d + 1) * (100.0 * d) / 2.0;
-    auto kern = event_kernel<SymGauss, d, VF_MODE_VEGAS, 52, true>;
+    auto kern = event_kernel<EXP_INTEGRAND, d, VF_MODE_VEGAS, 52, true>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     float best = 1e30f;

@@ -3,6 +3,7 @@
 // Reference citations are file:line relative to /root/reference.
 #pragma once
 #include <atomic>
+#include <type_traits>
 
 #include "vf_common.cuh"
 #include "vf_integrands.cuh"
@@ -21,14 +22,15 @@ namespace vf {
 //   * histogram copies are what the shared-memory atomics need most: HC = 32 (one copy per
 //     lane, no same-address collisions inside a warp) wherever it fits, else 16; the table gets
 //     what is left of the 227 KB (TC = 16 up to d = 8, 8 up to d = 12 and d = 15 ... 18, else 4);
-//   * heavy integrands (matrix elements) keep 512 threads and the 128-register budget.
+//   * heavy integrands keep 512 threads and the 128-register budget unless they name a block
+//     size themselves (`kBlockThreads`: Drell-Yan runs 768 x 80 registers, +12 %).
 constexpr size_t kSmemBudget = 227 * 1024 - 2048;  // opt-in limit minus static + reserved
 constexpr size_t cfg_smem_bytes(int n_dim, int tc, int hc) {
     return (size_t)n_dim * kBins * (16 * tc + 8 * hc);
 }
-template <int NDIM, bool HEAVY>
+template <int NDIM, bool HEAVY, int THREADS = 0>
 struct CfgT {
-    static constexpr int kThreads = HEAVY ? 512 : (NDIM >= 19 ? 768 : 1024);
+    static constexpr int kThreads = THREADS ? THREADS : (HEAVY ? 512 : (NDIM >= 19 ? 768 : 1024));
     static constexpr int HC = cfg_smem_bytes(NDIM, 4, 32) <= kSmemBudget ? 32 : 16;
     static constexpr int TC = (NDIM <= 8 && cfg_smem_bytes(NDIM, 16, HC) <= kSmemBudget)
                                   ? 16
@@ -38,8 +40,17 @@ struct CfgT {
     static constexpr size_t kSmemBytes = cfg_smem_bytes(NDIM, TC, HC);
     static_assert(kSmemBytes <= kSmemBudget, "n_dim too large for the fused kernels");
 };
+// an integrand may fix its block size with `static constexpr int kBlockThreads`
+template <class I, class = void>
+struct BlockThreadsOf {
+    static constexpr int value = 0;
+};
+template <class I>
+struct BlockThreadsOf<I, std::void_t<decltype(I::kBlockThreads)>> {
+    static constexpr int value = I::kBlockThreads;
+};
 template <class I, int NDIM>
-using Cfg = CfgT<NDIM, I::kHeavy>;
+using Cfg = CfgT<NDIM, I::kHeavy, BlockThreadsOf<I>::value>;
 
 struct EventKernelArgs {
     const double* divisions;  // [NDIM][51]

@@ -257,7 +257,10 @@ __device__ __forceinline__ cplx sdot(const Spin2& bra, const Spin2& ket) {
 // ---------------------------------------------------------------------------
 struct DrellYanLO {
     static constexpr int kFixedDim = 4;
-    static constexpr bool kHeavy = true;  // register-hungry: one block per SM
+    static constexpr bool kHeavy = true;
+    // measured (profiles/r2_me_threads.txt): 768 threads x 80 registers beat 512 x 116 by 12 %
+    // since the half-angle rewrite shortened the live ranges
+    static constexpr int kBlockThreads = 768;
     template <int NDIM>
     static __device__ double eval(const double (&xa)[NDIM], const IntegrandConsts&) {
         static_assert(NDIM == 4, "drellyan_lo is 4-dimensional");
@@ -329,7 +332,7 @@ struct DrellYanLO {
 // ---------------------------------------------------------------------------
 struct SingleTopLO {
     static constexpr int kFixedDim = 3;
-    static constexpr bool kHeavy = true;
+    static constexpr bool kHeavy = true;  // 512 threads x 128 registers (640 x 96: +1 %, noise)
 
     struct AllSpin {
         Spin2 up, um, bp, bm;  // u0(+1), u0(-1), ubar0(+1), ubar0(-1)
