@@ -91,59 +91,48 @@ class VegasFlow(MonteCarloFlow):
         self.train = True
         self._recompile()
 
+    # -- grid persistence -------------------------------------------------------------------
+    # File format of the reference (vflow.py:271-347), kept key for key so that grids written by
+    # either implementation load in the other: {"dimensions", "ALPHA", "BINS", "integrand", "grid"}.
+    def _integrand_label(self):
+        return getattr(self._integrand, "__name__", "") if self._integrand else ""
+
     def save_grid(self, file_name):
-        """Save the `divisions` array in a json file (vflow.py:271-292, same schema)."""
-        div_np = self.divisions.detach().cpu().numpy()
-        int_name = self._integrand.__name__ if self._integrand else ""
-        json_dict = {
-            "dimensions": self.n_dim,
-            "ALPHA": ALPHA,
-            "BINS": self.grid_bins,
-            "integrand": int_name,
-            "grid": div_np.tolist(),
-        }
-        with open(file_name, "w") as f:
-            json.dump(json_dict, f, indent=True)
+        """Write the grid to `file_name` as json (same schema as the reference, vflow.py:271-292)."""
+        payload = dict(dimensions=self.n_dim, ALPHA=ALPHA, BINS=self.grid_bins,
+                       integrand=self._integrand_label(),
+                       grid=self.divisions.detach().cpu().numpy().tolist())
+        with open(file_name, "w") as fh:
+            json.dump(payload, fh, indent=True)
+
+    def _check_grid_shape(self, n_dim, n_bins):
+        """ValueError on a grid of the wrong shape (the reference's checks, vflow.py:330-341)."""
+        for what, got, have in (("dimensions", n_dim, self.n_dim), ("bins", n_bins, self.grid_bins)):
+            if got is not None and got != have:
+                raise ValueError(f"The grid to load has {got} {what}, this integrator was "
+                                 f"instantiated with {have}")
 
     def load_grid(self, file_name=None, numpy_grid=None):
-        """Load the `divisions` array from a json file or a numpy array (vflow.py:294-347)."""
-        if file_name is not None and numpy_grid is not None:
-            raise ValueError(
-                "Received both a numpy grid and a file_name to load the grid from."
-                "Ambiguous call to `load_grid`"
-            )
-        if file_name:
-            with open(file_name, "r") as f:
-                json_dict = json.load(f)
-            grid_dim = json_dict.get("dimensions")
-            grid_bins = json_dict.get("BINS")
-            if self._integrand:
-                integrand_name = self._integrand.__name__
-                integrand_grid = json_dict.get("integrand")
-                if integrand_name != integrand_grid:
-                    logger.warning(
-                        f"The grid was written for the integrand: {integrand_grid}"
-                        f"which is different from {integrand_name}"
-                    )
-            numpy_grid = np.array(json_dict["grid"])
-        elif numpy_grid is not None:
-            grid_dim = numpy_grid.shape[0]
-            grid_bins = numpy_grid.shape[1]
-        else:
-            raise ValueError("load_grid was called but no grid was provided!")
-        if grid_dim is not None and self.n_dim != grid_dim:
-            raise ValueError(
-                f"Received a {grid_dim}-dimensional grid while VegasFlow"
-                f"was instantiated with {self.n_dim} dimensions"
-            )
-        if grid_bins is not None and self.grid_bins != grid_bins:
-            raise ValueError(
-                f"The received grid contains {grid_bins} bins while the"
-                f"current settings is of {self.grid_bins} bins"
-            )
-        if file_name:
+        """Take the grid from a json file written by `save_grid` or from a `(n_dim, bins)` array
+        (vflow.py:294-347: exactly one of the two, shape checked against the instance)."""
+        if (file_name is None) == (numpy_grid is None):
+            if file_name is None:
+                raise ValueError("load_grid was called but no grid was provided!")
+            raise ValueError("load_grid takes either a file name or a numpy grid, not both")
+        if file_name is not None:
+            with open(file_name, "r") as fh:
+                stored = json.load(fh)
+            grid = np.array(stored["grid"])
+            self._check_grid_shape(stored.get("dimensions"), stored.get("BINS"))
+            written_for = stored.get("integrand")
+            if self._integrand and written_for != self._integrand_label():
+                logger.warning(f"The grid was written for the integrand {written_for!r}, "
+                               f"the current one is {self._integrand_label()!r}")
             logger.info(f" > SUCCESS: Loaded grid from {file_name}")
-        self._divisions_host = np.ascontiguousarray(numpy_grid, dtype=np.float64)
+        else:
+            grid = np.asarray(numpy_grid)
+            self._check_grid_shape(grid.shape[0], grid.shape[1])
+        self._divisions_host = np.ascontiguousarray(grid, dtype=np.float64)
         if self._divisions_dev is not None:
             self._divisions_dev.copy_(torch.from_numpy(self._divisions_host))
 
