@@ -201,6 +201,30 @@ def test_fused_event_kernel_against_oracle_same_stream(lib, name, d):
     assert f1 == s1 and f2 == s2
 
 
+@pytest.mark.parametrize("d", [1, 8, 20])
+def test_fused_event_kernel_ragged_tiny_and_counter_wrap(lib, d):
+    """Edge cases of the event range: empty, a single event, one short of / one past a warp and a
+    block, a count that is no multiple of anything, and a range that crosses the 2^32 boundary of
+    the Philox event counter (the high counter word changes in the middle of the launch)."""
+    rng = np.random.default_rng(100 + d)
+    grid = np.sort(rng.random((d, 51)), axis=1)
+    grid[:, 0], grid[:, -1] = 0.0, 1.0
+    seed, it = 99, 2
+    cases = [(0, 0), (0, 1), (5, 31), (0, 32), (7, 33), (0, 1023), (3, 1025), (0, 151553),
+             (2**32 - 1000, 3000), (2**40 + 17, 70001)]
+    for ev_begin, n in cases:
+        s1, s2, hist = gpu_run_event(lib, 1, 0, d, ev_begin, n, 1e-3, seed, it, True, grid)
+        if n == 0:
+            assert s1 == 0.0 and s2 == 0.0 and not hist.any()
+            continue
+        o1, o2, ohist = co.run_event(co.MODE_VEGAS, "symgauss", d, ev_begin, n, 1e-3, seed, it,
+                                     True, grid)
+        assert abs(s1 - o1) <= 1e-11 * abs(o1), (ev_begin, n)
+        assert abs(s2 - o2) <= 1e-11 * abs(o2), (ev_begin, n)
+        np.testing.assert_allclose(hist, ohist, rtol=1e-10, atol=1e-300)
+        np.testing.assert_allclose(hist.sum(axis=1), np.full(d, s2), rtol=1e-11)
+
+
 def test_fused_event_kernel_plain_and_limits(lib):
     n, d = 200000, 3
     xmin, xmax = np.array([-1.0, 0.5, 2.0]), np.array([1.0, 1.5, 2.25])
