@@ -254,6 +254,8 @@ __device__ __forceinline__ void vegas_map_dim_s(double xn, uint32_t tbl_s, uint3
     bin = __double2loint(t);
     const double fl = __dsub_rn(t, kTwo52);   // tf.math.floor(xn), vflow.py:75
     const double aux = __dsub_rn(xn, fl);     // :75
+    // (forming the row address on the fp64 pipe instead -- the low word of fl*PITCH + (2^52 + base),
+    // one DFMA for the IMAD -- is 2 % slower: profiles/r2_k1_r3_floor_exp_variants.txt)
     row = row_addr<TC * 16>(bin, tbl_s);
     const double2 e = lds_f64x2(row, off);
     x = __dadd_rn(e.x, __dmul_rn(e.y, aux));  // :76, mul then add
