@@ -4,6 +4,8 @@
 // Reference citations are file:line relative to /root/reference.
 #include <cstdlib>
 
+#include <cooperative_groups.h>
+
 #include "vf_aux.cuh"
 
 namespace vf {
@@ -914,6 +916,175 @@ __device__ void plus_cube_block(const PlusTailArgs& a, const Xchg& xc) {
     }
 }
 
+// ---------------------------------------------------------------------------
+// Single-GPU VEGAS+ tail on a thread-block CLUSTER (sm_90+): the per-cube pass of
+// plus_cube_block spread over 8 CTAs x 1024 threads -- one cube per thread at the reference's cap
+// of 10^4 cubes -- with the block totals exchanged through distributed shared memory.  One block
+// needed ~7 pow() per thread, three 32-step serial block sums and a 10-step Hillis-Steele scan
+// (36 us per iteration, 3 % of the c3 step); the cluster does one pow() per thread, shuffle
+// scans, and three cluster barriers.  Every sum is taken in a fixed order (thread slice -> warp
+// butterfly -> warps 0..31 -> CTAs 0..7), so the allocation stays a pure function of its inputs.
+// ---------------------------------------------------------------------------
+constexpr int kCubeCluster = 8;
+
+struct ClusterScratch {
+    double warp_part[kPlusThreads / 32];
+    double cta_total[4];     // one slot per cluster-wide sum (no slot is reused)
+    long long warp_count[kPlusThreads / 32];
+    long long cta_count;
+};
+
+// fixed-order sum over the whole cluster of one value per thread; `slot` in 0..3
+__device__ double cluster_sum(double v, ClusterScratch& sc, int slot) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = warp_sum(v);
+    if (lane == 0) sc.warp_part[warp] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < kPlusThreads / 32; ++k) t += sc.warp_part[k];
+        sc.cta_total[slot] = t;
+    }
+    cluster.sync();  // also orders the reuse of warp_part by the next call
+    double tot = 0.0;
+    for (unsigned r = 0; r < cluster.num_blocks(); ++r)
+        tot += *cluster.map_shared_rank(&sc.cta_total[slot], r);
+    return tot;
+}
+
+__device__ void plus_cube_cluster(const PlusTailArgs& a) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ ClusterScratch sc;
+    const unsigned crank = cluster.block_rank(), csize = cluster.num_blocks();
+    const int64_t nthreads = (int64_t)csize * kPlusThreads;
+    const int64_t gt = (int64_t)crank * kPlusThreads + threadIdx.x;
+    const int64_t per = (a.n_cubes + nthreads - 1) / nthreads;  // contiguous slice per thread
+    const int64_t c0 = imin64(gt * per, a.n_cubes), c1 = imin64(c0 + per, a.n_cubes);
+    double res = 0.0, sig2 = 0.0;
+    for (int64_t c = c0; c < c1; ++c) {
+        const double fn = (double)a.n_ev[c];
+        const double r1 = a.ress[c];
+        const double var = __dsub_rn(__dmul_rn(a.ress2[c], fn), __dmul_rn(r1, r1));  // :216-217
+        a.arr_var[c] = var;
+        res += r1;                                        // :231
+        sig2 += __ddiv_rn(fmax(var, 0.0), fn - 1.0);      // :230, :232
+        if (a.zero_sums) a.ress[c] = a.ress2[c] = 0.0;
+    }
+    res = cluster_sum(res, sc, 0);
+    sig2 = cluster_sum(sig2, sc, 1);
+    constexpr int kKeep = 4;  // one cube per thread up to 8192 cubes, two up to 16384, ...
+    const bool keep = per <= kKeep;
+    double dv[kKeep];
+    double damp = 0.0;
+    if (a.adaptive) {
+        if (keep) {
+#pragma unroll
+            for (int k = 0; k < kKeep; ++k) {
+                dv[k] = 0.0;
+                if (c0 + k < c1) {
+                    dv[k] = pow(fmax(a.arr_var[c0 + k], 0.0), kBeta / 2);  // :157 (clamped)
+                    damp += dv[k];
+                }
+            }
+        } else {
+            for (int64_t c = c0; c < c1; ++c) damp += pow(fmax(a.arr_var[c], 0.0), kBeta / 2);
+        }
+    }
+    const double dsum = a.adaptive ? cluster_sum(damp, sc, 2) : 0.0;
+    long long local = 0;
+    for (int64_t c = c0; c < c1; ++c) {
+        int32_t nv = a.n_ev[c];
+        if (a.adaptive && dsum > 0.0) {
+            double d = 0.0;
+            if (keep) {
+#pragma unroll
+                for (int k = 0; k < kKeep; ++k)
+                    if (c - c0 == k) d = dv[k];
+            } else {
+                d = pow(fmax(a.arr_var[c], 0.0), kBeta / 2);
+            }
+            const double want =
+                __ddiv_rn(__ddiv_rn(__dmul_rn(d, a.init_calls), 2.0), dsum);  // :160
+            nv = (int32_t)fmax((double)a.min_neval, want);                    // :158-162
+            a.n_ev[c] = nv;
+        }
+        local += nv;
+    }
+    // exclusive prefix of `local` over the cluster: warp shuffle scan, warp totals, CTA totals
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    long long incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+    }
+    if (lane == 31) sc.warp_count[warp] = incl;
+    __syncthreads();
+    long long before = 0, cta_tot = 0;
+    for (int k = 0; k < kPlusThreads / 32; ++k) {
+        const long long wv = sc.warp_count[k];
+        if (k < warp) before += wv;
+        cta_tot += wv;
+    }
+    if (threadIdx.x == 0) sc.cta_count = cta_tot;
+    cluster.sync();
+    long long cta_before = 0, total = 0;
+    for (unsigned r = 0; r < csize; ++r) {
+        const long long t = *cluster.map_shared_rank(&sc.cta_count, r);
+        if (r < crank) cta_before += t;
+        total += t;
+    }
+    if (a.adaptive && a.ev_offset) {
+        long long run = cta_before + before + (incl - local);
+        for (int64_t c = c0; c < c1; ++c) {
+            a.ev_offset[c] = run;
+            run += a.n_ev[c];
+        }
+        if (gt == 0) a.ev_offset[a.n_cubes] = total;
+    }
+    if (gt == 0) {
+        const double sigma = sqrt(sig2);  // :233
+        a.result[0] = res;
+        a.result[1] = sigma;
+        a.result[2] = (double)total;  // :163
+        if (a.result_host) {
+            a.result_host[0] = res;
+            a.result_host[1] = sigma;
+            a.result_host[2] = (double)total;
+        }
+        if (a.n_events_out) *a.n_events_out = total;
+    }
+    cluster.sync();  // no CTA may exit while its shared memory can still be read remotely
+}
+
+// Single-GPU tail of a VEGAS+ iteration with the cube pass on a cluster: the grid is a whole
+// number of 8-CTA clusters; the first ceil(n_dim/8) clusters hold the histogram-row blocks
+// [0, n_dim) (their surplus blocks exit at once, nobody synchronises there), the LAST cluster is
+// plus_cube_cluster.
+__global__ void __launch_bounds__(kPlusThreads) plus_iteration_cluster_kernel(
+    double* __restrict__ workspace, int nblocks, int n_dim, int train, double* out_hist,
+    double* divisions, const __grid_constant__ PlusTailArgs a) {
+    __shared__ double row[64];
+    pdl_launch_dependents();
+    pdl_wait();
+    if (blockIdx.x >= gridDim.x - kCubeCluster) {
+        plus_cube_cluster(a);
+        return;
+    }
+    const int blk = blockIdx.x, col = threadIdx.x;
+    if (!train || blk >= n_dim) return;
+    if (col < kBins) {
+        const double tot = gather_column(workspace, nblocks, false, blk, nullptr);
+        out_hist[(size_t)blk * kBins + col] = tot;
+        row[col] = tot;
+    }
+    __syncthreads();
+    refine_dimension(row, divisions + (size_t)blk * kEdges);
+}
+
 // Stand-alone form (vfp_iteration_epilogue): `result` has room for two doubles only.
 __global__ void __launch_bounds__(kPlusThreads) plus_epilogue_kernel(
     const __grid_constant__ PlusTailArgs a, const __grid_constant__ Xchg xc, double* result2) {
@@ -1004,8 +1175,17 @@ int launch_plus_iteration_tail(double* workspace, int nblocks, int n_dim, int tr
                                      ev_offset, arr_var, result, result_host, nullptr, 1);
     const Xchg xc = make_xchg(n_dim, world > 1 ? n_cubes : 0, rank, world, peers, seq);
     timing_begin(stream, 1);
-    VF_CUDA_CHECK(launch_pdl(plus_iteration_kernel, train ? n_dim + 1 : 1, kPlusThreads, 0, stream,
-                             workspace, nblocks, n_dim, train, out_hist, divisions, a, xc));
+    if (world == 1) {  // cube pass on an 8-CTA cluster (distributed shared memory)
+        const int row_clusters = train ? (n_dim + kCubeCluster - 1) / kCubeCluster : 0;
+        VF_CUDA_CHECK(launch_pdl_cluster(plus_iteration_cluster_kernel,
+                                         (row_clusters + 1) * kCubeCluster, kPlusThreads,
+                                         kCubeCluster, stream, workspace, nblocks, n_dim, train,
+                                         out_hist, divisions, a));
+    } else {
+        VF_CUDA_CHECK(launch_pdl(plus_iteration_kernel, train ? n_dim + 1 : 1, kPlusThreads, 0,
+                                 stream, workspace, nblocks, n_dim, train, out_hist, divisions, a,
+                                 xc));
+    }
     timing_end(stream, 1);
     count_launch();
     return VF_OK;
