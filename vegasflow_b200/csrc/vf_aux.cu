@@ -747,7 +747,7 @@ int launch_accumulate(int n_dim, int64_t n, const double* w, const double* f, co
 // ---------------------------------------------------------------------------
 // VEGAS+ iteration tail: arr_var (vflowplus.py:216-217), res/sigma (:230-233),
 // redistribute_samples (:153-163) and the new event offsets -- one block of 1024 threads;
-// fused with the histogram reduction + grid refinement blocks in plus_iteration_kernel.
+// the stand-alone form behind vfp_iteration_epilogue (the iteration chain uses plus_cube_cluster).
 //
 // Multi-GPU (the reference is single-device, vflowplus.py:88-100): rank r owns
 // the contiguous cube range whose events are [~n*r/R, ~n*(r+1)/R) (boundaries on cube edges,
@@ -917,7 +917,7 @@ __device__ void plus_cube_block(const PlusTailArgs& a, const Xchg& xc) {
 }
 
 // ---------------------------------------------------------------------------
-// Single-GPU VEGAS+ tail on a thread-block CLUSTER (sm_90+): the per-cube pass of
+// VEGAS+ tail on a thread-block CLUSTER (sm_90+): the per-cube pass of
 // plus_cube_block spread over 8 CTAs x 1024 threads -- one cube per thread at the reference's cap
 // of 10^4 cubes -- with the block totals exchanged through distributed shared memory.  One block
 // needed ~7 pow() per thread, three 32-step serial block sums and a 10-step Hillis-Steele scan
@@ -930,6 +930,7 @@ constexpr int kCubeCluster = 8;
 struct ClusterScratch {
     double warp_part[kPlusThreads / 32];
     double cta_total[4];     // one slot per cluster-wide sum (no slot is reused)
+    double xtot[2];          // multi-GPU: (res, sigma^2) summed over the ranks, held by CTA 0
     long long warp_count[kPlusThreads / 32];
     long long cta_count;
 };
@@ -954,7 +955,7 @@ __device__ double cluster_sum(double v, ClusterScratch& sc, int slot) {
     return tot;
 }
 
-__device__ void plus_cube_cluster(const PlusTailArgs& a) {
+__device__ void plus_cube_cluster(const PlusTailArgs& a, const Xchg& xc) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
     __shared__ ClusterScratch sc;
@@ -963,23 +964,58 @@ __device__ void plus_cube_cluster(const PlusTailArgs& a) {
     const int64_t gt = (int64_t)crank * kPlusThreads + threadIdx.x;
     const int64_t per = (a.n_cubes + nthreads - 1) / nthreads;  // contiguous slice per thread
     const int64_t c0 = imin64(gt * per, a.n_cubes), c1 = imin64(c0 + per, a.n_cubes);
+    // multi-GPU: this rank holds the sums of the cubes [lo, hi) only (see plus_cube_block)
+    const bool multi = xc.world > 1;
+    int64_t lo = 0, hi = a.n_cubes;
+    unsigned int flag = 0;
+    if (multi) {
+        flag = xchg_flag(xc);
+        const int64_t n = a.ev_offset[a.n_cubes];
+        lo = first_cube_at_or_after(a.ev_offset, a.n_cubes, n * xc.rank / xc.world);
+        hi = first_cube_at_or_after(a.ev_offset, a.n_cubes, n * (xc.rank + 1) / xc.world);
+    }
     double res = 0.0, sig2 = 0.0;
     for (int64_t c = c0; c < c1; ++c) {
-        const double fn = (double)a.n_ev[c];
-        const double r1 = a.ress[c];
-        const double var = __dsub_rn(__dmul_rn(a.ress2[c], fn), __dmul_rn(r1, r1));  // :216-217
-        a.arr_var[c] = var;
-        res += r1;                                        // :231
-        sig2 += __ddiv_rn(fmax(var, 0.0), fn - 1.0);      // :230, :232
+        if (c >= lo && c < hi) {
+            const double fn = (double)a.n_ev[c];
+            const double r1 = a.ress[c];
+            const double var = __dsub_rn(__dmul_rn(a.ress2[c], fn), __dmul_rn(r1, r1));  // :216-217
+            if (multi)
+                for (int p = 0; p < xc.world; ++p) ll_push(xchg_var_slot(xc, p, c), var, flag);
+            else
+                a.arr_var[c] = var;
+            res += r1;                                        // :231
+            sig2 += __ddiv_rn(fmax(var, 0.0), fn - 1.0);      // :230, :232
+        }
         if (a.zero_sums) a.ress[c] = a.ress2[c] = 0.0;
     }
     res = cluster_sum(res, sc, 0);
     sig2 = cluster_sum(sig2, sc, 1);
+    bool failed = false;
+    if (multi) {
+        // all-reduce of the rank partials (CTA 0), all-gather of the variances (every thread its
+        // slice: each value arrives flagged in the LOCAL buffer)
+        if (crank == 0 && threadIdx.x < 2)
+            sc.xtot[threadIdx.x] = xchg_allreduce_entry(
+                xc, xc.n_dim * kBins + threadIdx.x, threadIdx.x == 0 ? res : sig2);
+        bool ok = ld_sys_u64(xchg_poison(xc, xc.rank)) == 0ull;
+        for (int64_t c = c0; c < c1 && ok; ++c) {
+            double v;
+            ok = ll_wait(xc, xchg_var_slot(xc, xc.rank, c), flag, v);
+            a.arr_var[c] = v;
+        }
+        const double bad = cluster_sum(ok ? 0.0 : 1.0, sc, 3);  // its barrier publishes xtot
+        res = *cluster.map_shared_rank(&sc.xtot[0], 0);
+        sig2 = *cluster.map_shared_rank(&sc.xtot[1], 0);
+        failed = bad > 0.0 || res != res || sig2 != sig2;
+        if (failed) res = sig2 = __longlong_as_double(0x7ff8000000000000ll);
+    }
+    const bool adaptive = a.adaptive && !failed;
     constexpr int kKeep = 4;  // one cube per thread up to 8192 cubes, two up to 16384, ...
     const bool keep = per <= kKeep;
     double dv[kKeep];
     double damp = 0.0;
-    if (a.adaptive) {
+    if (adaptive) {
         if (keep) {
 #pragma unroll
             for (int k = 0; k < kKeep; ++k) {
@@ -993,11 +1029,11 @@ __device__ void plus_cube_cluster(const PlusTailArgs& a) {
             for (int64_t c = c0; c < c1; ++c) damp += pow(fmax(a.arr_var[c], 0.0), kBeta / 2);
         }
     }
-    const double dsum = a.adaptive ? cluster_sum(damp, sc, 2) : 0.0;
+    const double dsum = a.adaptive ? cluster_sum(damp, sc, 2) : 0.0;  // uniform over the cluster
     long long local = 0;
     for (int64_t c = c0; c < c1; ++c) {
         int32_t nv = a.n_ev[c];
-        if (a.adaptive && dsum > 0.0) {
+        if (adaptive && dsum > 0.0) {
             double d = 0.0;
             if (keep) {
 #pragma unroll
@@ -1060,60 +1096,23 @@ __device__ void plus_cube_cluster(const PlusTailArgs& a) {
     cluster.sync();  // no CTA may exit while its shared memory can still be read remotely
 }
 
-// Single-GPU tail of a VEGAS+ iteration with the cube pass on a cluster: the grid is a whole
-// number of 8-CTA clusters; the first ceil(n_dim/8) clusters hold the histogram-row blocks
-// [0, n_dim) (their surplus blocks exit at once, nobody synchronises there), the LAST cluster is
-// plus_cube_cluster.
+// Tail of a VEGAS+ iteration with the cube pass on a cluster: the grid is a whole number of 8-CTA
+// clusters; the first ceil(n_dim/8) clusters hold the histogram-row blocks [0, n_dim) (reduce,
+// multi-GPU exchange, refine; their surplus blocks exit at once, nobody synchronises there), the
+// LAST cluster is plus_cube_cluster.
 __global__ void __launch_bounds__(kPlusThreads) plus_iteration_cluster_kernel(
-    double* __restrict__ workspace, int nblocks, int n_dim, int train, double* out_hist,
-    double* divisions, const __grid_constant__ PlusTailArgs a) {
-    __shared__ double row[64];
-    pdl_launch_dependents();
-    pdl_wait();
-    if (blockIdx.x >= gridDim.x - kCubeCluster) {
-        plus_cube_cluster(a);
-        return;
-    }
-    const int blk = blockIdx.x, col = threadIdx.x;
-    if (!train || blk >= n_dim) return;
-    if (col < kBins) {
-        const double tot = gather_column(workspace, nblocks, false, blk, nullptr);
-        out_hist[(size_t)blk * kBins + col] = tot;
-        row[col] = tot;
-    }
-    __syncthreads();
-    refine_dimension(row, divisions + (size_t)blk * kEdges);
-}
-
-// Stand-alone form (vfp_iteration_epilogue): `result` has room for two doubles only.
-__global__ void __launch_bounds__(kPlusThreads) plus_epilogue_kernel(
-    const __grid_constant__ PlusTailArgs a, const __grid_constant__ Xchg xc, double* result2) {
-    __shared__ double res3[3];
-    PlusTailArgs b = a;
-    b.result = res3;
-    plus_cube_block(b, xc);
-    if (threadIdx.x == 0) {
-        result2[0] = res3[0];
-        result2[1] = res3[1];
-    }
-}
-
-// Whole tail of a VEGAS+ iteration in one launch: blocks [0, n_dim) reduce (and, multi-GPU,
-// exchange) one histogram row each and refine that dimension (only when training), the last
-// block is plus_cube_block.
-__global__ void __launch_bounds__(kPlusThreads) plus_iteration_kernel(
     double* __restrict__ workspace, int nblocks, int n_dim, int train, double* out_hist,
     double* divisions, const __grid_constant__ PlusTailArgs a, const __grid_constant__ Xchg xc) {
     __shared__ double row[64];
     __shared__ int failed;
     pdl_launch_dependents();
     pdl_wait();
-    const int cube_block = train ? n_dim : 0;
-    if ((int)blockIdx.x == cube_block) {
-        plus_cube_block(a, xc);
+    if (blockIdx.x >= gridDim.x - kCubeCluster) {
+        plus_cube_cluster(a, xc);
         return;
     }
     const int blk = blockIdx.x, col = threadIdx.x;
+    if (!train || blk >= n_dim) return;
     if (col == 0) failed = 0;
     __syncthreads();
     if (col < kBins) {
@@ -1127,6 +1126,19 @@ __global__ void __launch_bounds__(kPlusThreads) plus_iteration_kernel(
     }
     __syncthreads();
     if (!failed) refine_dimension(row, divisions + (size_t)blk * kEdges);
+}
+
+// Stand-alone form (vfp_iteration_epilogue): `result` has room for two doubles only.
+__global__ void __launch_bounds__(kPlusThreads) plus_epilogue_kernel(
+    const __grid_constant__ PlusTailArgs a, const __grid_constant__ Xchg xc, double* result2) {
+    __shared__ double res3[3];
+    PlusTailArgs b = a;
+    b.result = res3;
+    plus_cube_block(b, xc);
+    if (threadIdx.x == 0) {
+        result2[0] = res3[0];
+        result2[1] = res3[1];
+    }
 }
 
 static PlusTailArgs make_tail(int64_t n_cubes, double* ress, double* ress2, int adaptive,
@@ -1175,17 +1187,12 @@ int launch_plus_iteration_tail(double* workspace, int nblocks, int n_dim, int tr
                                      ev_offset, arr_var, result, result_host, nullptr, 1);
     const Xchg xc = make_xchg(n_dim, world > 1 ? n_cubes : 0, rank, world, peers, seq);
     timing_begin(stream, 1);
-    if (world == 1) {  // cube pass on an 8-CTA cluster (distributed shared memory)
-        const int row_clusters = train ? (n_dim + kCubeCluster - 1) / kCubeCluster : 0;
-        VF_CUDA_CHECK(launch_pdl_cluster(plus_iteration_cluster_kernel,
-                                         (row_clusters + 1) * kCubeCluster, kPlusThreads,
-                                         kCubeCluster, stream, workspace, nblocks, n_dim, train,
-                                         out_hist, divisions, a));
-    } else {
-        VF_CUDA_CHECK(launch_pdl(plus_iteration_kernel, train ? n_dim + 1 : 1, kPlusThreads, 0,
-                                 stream, workspace, nblocks, n_dim, train, out_hist, divisions, a,
-                                 xc));
-    }
+    // cube pass on an 8-CTA cluster (distributed shared memory), single- and multi-GPU
+    const int row_clusters = train ? (n_dim + kCubeCluster - 1) / kCubeCluster : 0;
+    VF_CUDA_CHECK(launch_pdl_cluster(plus_iteration_cluster_kernel,
+                                     (row_clusters + 1) * kCubeCluster, kPlusThreads, kCubeCluster,
+                                     stream, workspace, nblocks, n_dim, train, out_hist, divisions,
+                                     a, xc));
     timing_end(stream, 1);
     count_launch();
     return VF_OK;
