@@ -209,26 +209,6 @@ __device__ __forceinline__ Angles angles_acos(const Mom& p) {
     return a;
 }
 
-// theta/phi of singletop u0 (:110-129): phi in {0, pi} from the sign of px/E.
-__device__ __forceinline__ Angles angles_st_u0(const Mom& p) {
-    const double rz = p.z / p.e;
-    Angles a;
-    a.cp = 1.0;
-    a.sp = 0.0;
-    if (p.x == 0.0) {
-        half_angle_axis(rz, a.ch, a.sh);
-    } else {
-        const double theta = acos(clip1(rz));
-        sincos(theta / 2, &a.sh, &a.ch);
-        if (p.x / p.e < 0.0) {  // phi = pi: the reference's np.cos(np.pi), np.sin(np.pi)
-            a.cp = -1.0;
-            a.sp = kSinPi;
-        }
-    }
-    a.pref = spinor_prefact(p.e);
-    return a;
-}
-
 struct Spin2 {
     cplx a, b;  // the two non-zero components
 };
@@ -337,9 +317,17 @@ struct SingleTopLO {
     struct AllSpin {
         Spin2 up, um, bp, bm;  // u0(+1), u0(-1), ubar0(+1), ubar0(-1)
     };
+    // u0 and ubar0 of one momentum share theta (singletop :110-129 and :156-178 both start from
+    // acos(clip(pz/E)) and need sincos(theta/2)): evaluated once, the same operations
     static __device__ __forceinline__ AllSpin spinors(const Mom& p) {
-        const Angles gu = angles_st_u0(p);
-        const Angles gb = angles_acos(p);
+        Angles gb = angles_acos(p);
+        Angles gu = gb;      // same theta -> same (ch, sh, pref)
+        gu.cp = 1.0;         // phi of u0 is 0 or pi from the sign of px/E (:124-126)
+        gu.sp = 0.0;
+        if (p.x != 0.0 && p.x / p.e < 0.0) {
+            gu.cp = -1.0;    // the reference's np.cos(np.pi), np.sin(np.pi)
+            gu.sp = kSinPi;
+        }
         return {u0_plus(gu), u0_minus(gu), ubar0_plus(gb), ubar0_minus(gb)};
     }
     // sprod(p1,p2) = Re(za(p1,p2)*zb(p2,p1)) :213-218
