@@ -176,7 +176,7 @@ __device__ __forceinline__ Angles angles_half(const Mom& p) {
         a.cp = cx;
         a.sp = sqrt((1.0 - cx) * (1.0 + cx));
         if (cx == -1.0) a.sp = kSinPi;  // phi == pi: the reference's sin(np.pi)
-        if (p.y / p.e < 0.0) a.sp = -a.sp;
+        if (p.e > 0.0 ? (p.y < 0.0) : (p.y / p.e < 0.0)) a.sp = -a.sp;  // sign of py/E
         if (cx == 1.0) a.sp = 0.0;  // phi == 0 (also -0): cos 0 = 1, sin 0 = 0
     }
     a.pref = spinor_prefact(p.e);
@@ -189,22 +189,28 @@ __device__ __forceinline__ Angles angles_half(const Mom& p) {
 // 2e-16 / cos(theta/2) that reaches 1e-8 -- amplitudes proportional to it agree with the
 // reference to 1e-12 only if theta is rounded the same way (0.4 % of uniformly drawn events would
 // miss the bar with the more accurate half-angle forms).  Drell-Yan has no such region.
-__device__ __forceinline__ Angles angles_acos(const Mom& p) {
+// `pxe` returns px/E (0 on the beam axis) for the caller that needs its sign again.
+__device__ __forceinline__ Angles angles_acos(const Mom& p, double* pxe = nullptr) {
     const double rz = p.z / p.e;
     Angles a;
     a.cp = 1.0;  // phi == 0 (beam-axis momenta, and phi2 == 0): cos 0 = 1, sin 0 = 0
     a.sp = 0.0;
+    double rxe = 0.0;
     if (p.x == 0.0) {
         half_angle_axis(rz, a.ch, a.sh);  // theta1 in {0, pi}: sincos(theta/2) are constants
     } else {
         const double theta = acos(clip1(rz));
-        const double rx = p.x / p.e / sin(theta);
+        rxe = p.x / p.e;
+        const double rx = rxe / sin(theta);
         double phi = acos(clip1(rx));
-        const double ry = p.y / p.e;
-        if (ry < 0.0) phi = -phi;
+        // py/E < 0: with E > 0 (every physical momentum) that is py < 0, no division needed;
+        // the quotient is formed only for E <= 0 or NaN, where its sign rules apply
+        const bool neg = p.e > 0.0 ? (p.y < 0.0) : (p.y / p.e < 0.0);
+        if (neg) phi = -phi;
         sincos(theta / 2, &a.sh, &a.ch);  // one argument reduction for both
         if (phi != 0.0) sincos(phi, &a.sp, &a.cp);
     }
+    if (pxe) *pxe = rxe;
     a.pref = spinor_prefact(p.e);
     return a;
 }
@@ -320,11 +326,12 @@ struct SingleTopLO {
     // u0 and ubar0 of one momentum share theta (singletop :110-129 and :156-178 both start from
     // acos(clip(pz/E)) and need sincos(theta/2)): evaluated once, the same operations
     static __device__ __forceinline__ AllSpin spinors(const Mom& p) {
-        Angles gb = angles_acos(p);
+        double pxe;
+        Angles gb = angles_acos(p, &pxe);
         Angles gu = gb;      // same theta -> same (ch, sh, pref)
         gu.cp = 1.0;         // phi of u0 is 0 or pi from the sign of px/E (:124-126)
         gu.sp = 0.0;
-        if (p.x != 0.0 && p.x / p.e < 0.0) {
+        if (pxe < 0.0) {     // (px/E is 0 on the beam axis)
             gu.cp = -1.0;    // the reference's np.cos(np.pi), np.sin(np.pi)
             gu.sp = kSinPi;
         }
@@ -381,7 +388,8 @@ struct SingleTopLO {
         const double x2 = sqrttau / expy;
         // make_event :71-92
         const double ecmo2 = sqrt(shat) / 2;
-        const double cc = ecmo2 * (1 - mt2 / shat);
+        const double one_m = 1 - mt2 / shat;  // used twice (:78, :88)
+        const double cc = ecmo2 * one_m;
         const double cosv = 1 - 2 * xa[2];
         const double sinxi = cc * sqrt(1 - cosv * cosv);
         const double cosxi = cc * cosv;
@@ -389,7 +397,7 @@ struct SingleTopLO {
         const Mom p1{ecmo2, 0.0, 0.0, -ecmo2};
         const Mom p2{cc, sinxi, 0.0, cosxi};
         Mom p3{sqrt(cc * cc + mt2), -sinxi, 0.0, -cosxi};
-        double psw = (1 - mt2 / shat) / (8.0 * M_PI);  // :88
+        double psw = one_m / (8.0 * M_PI);  // :88
         psw = psw * jac;
         const double flux = 1 / (2 * shat);
         // massless projection :236-239; dot :95-102
@@ -404,7 +412,7 @@ struct SingleTopLO {
         // luminosities :254-260
         const double pdf = x1 * x2;
         const double lumi1 = (pdf + pdf) / x1 / x2;
-        const double lumi2 = (pdf + pdf) / x1 / x2;
+        const double lumi2 = lumi1;  // the same expression in the reference (:257-260)
         const double lumi_me2 = 2 * lumi1 * c1 + 2 * lumi2 * c2;  // :267
         return lumi_me2 * psw * flux * conv;                       // :268
     }
