@@ -238,6 +238,40 @@ __device__ __forceinline__ cplx sdot(const Spin2& bra, const Spin2& ket) {
     return cadd(cmul(bra.a, ket.a), cmul(bra.b, ket.b));
 }
 
+// Beam-axis momenta.  Both examples build the spinors of -p1 = (-E, 0, 0, +E) and
+// -p0 = (-E, 0, 0, -E) with E = ecmo2 > 0: pz/E' is exactly -1 / +1, so theta is pi / 0, phi is
+// 0, and the generic construction multiplies by (cos phi, sin phi) = (1, 0), by sin(theta/2) = 1
+// or 0 and by cos(theta/2) = 6.12e-17 or 1 at run time.  Written out, the theta = 0 spinors have
+// ONE non-zero component (the other is pref * 0: an exact zero whose products and sums change
+// nothing), so every sdot() with them is one complex product instead of two.  Same values, bit
+// for bit, as the generic route (checked by the parity tests and the full-size checksums).
+struct SpinA {
+    cplx v;  // (v, 0)
+};
+struct SpinB {
+    cplx v;  // (0, v)
+};
+__device__ __forceinline__ cplx sdot(const Spin2& bra, const SpinA& ket) { return cmul(bra.a, ket.v); }
+__device__ __forceinline__ cplx sdot(const Spin2& bra, const SpinB& ket) { return cmul(bra.b, ket.v); }
+__device__ __forceinline__ cplx sdot(const SpinA& bra, const Spin2& ket) { return cmul(bra.v, ket.a); }
+__device__ __forceinline__ cplx sdot(const SpinB& bra, const Spin2& ket) { return cmul(bra.v, ket.b); }
+struct BeamSpin0 {   // theta = 0: u0(+1), u0(-1), ubar0(+1), ubar0(-1) of (E', 0, 0, E'), E' < 0
+    SpinA up;
+    SpinB um;
+    SpinA bp;
+    SpinB bm;
+};
+struct BeamSpinPi {  // theta = pi: of (E', 0, 0, -E')
+    Spin2 up, um, bp, bm;
+};
+__device__ __forceinline__ BeamSpin0 beam_spinors_theta0(cplx pref) {
+    return {SpinA{pref}, SpinB{cneg(pref)}, SpinA{pref}, SpinB{cneg(pref)}};
+}
+__device__ __forceinline__ BeamSpinPi beam_spinors_thetapi(cplx pref) {
+    const cplx small = cscale(pref, kCosHalfPi), nsmall = cscale(cneg(pref), kCosHalfPi);
+    return {Spin2{small, pref}, Spin2{pref, nsmall}, Spin2{small, pref}, Spin2{pref, nsmall}};
+}
+
 // ---------------------------------------------------------------------------
 // Drell-Yan LO, examples/drellyan_lo_tf.py:27-249 (n_dim = 4)
 // ---------------------------------------------------------------------------
@@ -288,18 +322,20 @@ struct DrellYanLO {
         psw = psw * jac;
         const double flux = 1 / (2 * mV2);
         // qqxllx(-p1, -p0, p2, p3) :207-224
-        const Mom q0 = mneg(p1), q1 = mneg(p0);
-        const Angles a0 = angles_half(q0), a1 = angles_half(q1), a2 = angles_half(p2),
-                     a3 = angles_half(p3);
+        // q0 = -p1 = (-ecmo2, 0, 0, +ecmo2): theta = pi; q1 = -p0 = (-ecmo2, 0, 0, -ecmo2): theta = 0
+        const cplx bpref = spinor_prefact(-ecmo2);
+        const BeamSpinPi s0 = beam_spinors_thetapi(bpref);
+        const BeamSpin0 s1 = beam_spinors_theta0(bpref);
+        const Angles a2 = angles_half(p2), a3 = angles_half(p3);
         // za(a,b) = ubar0(a,-1).u0(b,+1); zb(a,b) = ubar0(a,+1).u0(b,-1)
-        const Spin2 ubm0 = ubar0_minus(a0);
-        const cplx za01 = sdot(ubm0, u0_plus(a1));
-        const cplx zb10 = sdot(ubar0_plus(a1), u0_minus(a0));
+        const Spin2 ubm0 = s0.bm;
+        const cplx za01 = sdot(ubm0, s1.up);
+        const cplx zb10 = sdot(s1.bp, s0.um);
         const cplx sp = cmul(za01, zb10);
         const double lsprod = sp.re;  // sprod(p0,p1) :200-204
         const cplx za02 = sdot(ubm0, u0_plus(a2));
         const cplx za03 = sdot(ubm0, u0_plus(a3));
-        const Spin2 u1m = u0_minus(a1);
+        const SpinB u1m = s1.um;
         const cplx zb31 = sdot(ubar0_plus(a3), u1m);
         const cplx zb21 = sdot(ubar0_plus(a2), u1m);
         const double a = 2 * cabs(cmul(za02, zb31)) / lsprod;
@@ -338,17 +374,18 @@ struct SingleTopLO {
         }
         return {u0_plus(gu), u0_minus(gu), ubar0_plus(gb), ubar0_minus(gb)};
     }
-    // sprod(p1,p2) = Re(za(p1,p2)*zb(p2,p1)) :213-218
-    static __device__ __forceinline__ double sprod(const AllSpin& s1, const AllSpin& s2) {
+    // sprod(p1,p2) = Re(za(p1,p2)*zb(p2,p1)) :213-218 (any mix of generic and beam spinor sets)
+    template <class S1, class S2>
+    static __device__ __forceinline__ double sprod(const S1& s1, const S2& s2) {
         const cplx za = sdot(s1.bm, s2.up);
         const cplx zb = sdot(s2.bp, s1.um);
         return cmul(za, zb).re;
     }
     // qqxtbx :221-230
-    static __device__ __forceinline__ double qqxtbx(const AllSpin& p0, const AllSpin& p1,
-                                                    const AllSpin& p2, const AllSpin& p3,
-                                                    double mt2, double mw2, double gaw2,
-                                                    double gw4) {
+    template <class S0, class S1, class S2, class S3>
+    static __device__ __forceinline__ double qqxtbx(const S0& p0, const S1& p1, const S2& p2,
+                                                    const S3& p3, double mt2, double mw2,
+                                                    double gaw2, double gw4) {
         const double pw2 = sprod(p0, p1);
         const double d0 = pw2 - mw2;
         const double wprop = d0 * d0 + mw2 * gaw2;
@@ -406,8 +443,11 @@ struct SingleTopLO {
         const double k = mt2 / dot30 / 2;
         p3 = Mom{p3.e - p0.e * k, p3.x - p0.x * k, p3.y - p0.y * k, p3.z - p0.z * k};
         // channels :242-245
-        const AllSpin A = spinors(p2), B = spinors(mneg(p1)), Cc = spinors(p3),
-                      D = spinors(mneg(p0));
+        // -p1 = (-ecmo2, 0, 0, +ecmo2): theta = pi; -p0 = (-ecmo2, 0, 0, -ecmo2): theta = 0
+        const cplx bpref = spinor_prefact(-ecmo2);
+        const AllSpin A = spinors(p2), Cc = spinors(p3);
+        const BeamSpinPi B = beam_spinors_thetapi(bpref);
+        const BeamSpin0 D = beam_spinors_theta0(bpref);
         const double c1 = qqxtbx(A, B, Cc, D, mt2, mw2, gaw2, gw4);
         const double c2 = qqxtbx(B, A, Cc, D, mt2, mw2, gaw2, gw4);
         // luminosities :254-260
