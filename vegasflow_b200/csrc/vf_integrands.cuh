@@ -6,6 +6,14 @@
 #pragma once
 #include "vf_common.cuh"
 
+// block sizes of the matrix-element kernels (tunable at build time; measured defaults)
+#ifndef VF_DY_THREADS
+#define VF_DY_THREADS 1024
+#endif
+#ifndef VF_ST_THREADS
+#define VF_ST_THREADS 640
+#endif
+
 namespace vf {
 
 // ---------------------------------------------------------------------------
@@ -278,9 +286,9 @@ __device__ __forceinline__ BeamSpinPi beam_spinors_thetapi(cplx pref) {
 struct DrellYanLO {
     static constexpr int kFixedDim = 4;
     static constexpr bool kHeavy = true;
-    // measured (profiles/r2_me_threads.txt): 768 threads x 80 registers beat 512 x 116 by 12 %
+    // measured (profiles/r2_me_threads.txt): 1024 threads x 64 registers beat 512 x 116 by 14 %
     // since the half-angle rewrite shortened the live ranges
-    static constexpr int kBlockThreads = 768;
+    static constexpr int kBlockThreads = VF_DY_THREADS;
     template <int NDIM>
     static __device__ double eval(const double (&xa)[NDIM], const IntegrandConsts&) {
         static_assert(NDIM == 4, "drellyan_lo is 4-dimensional");
@@ -355,7 +363,7 @@ struct DrellYanLO {
 struct SingleTopLO {
     static constexpr int kFixedDim = 3;
     static constexpr bool kHeavy = true;
-    static constexpr int kBlockThreads = 640;  // 640 x 96 registers: +1.4 % over 512 x 128
+    static constexpr int kBlockThreads = VF_ST_THREADS;  // 640 x 96 registers: +1.4 % over 512 x 128
 
     struct AllSpin {
         Spin2 up, um, bp, bm;  // u0(+1), u0(-1), ubar0(+1), ubar0(-1)
