@@ -337,6 +337,12 @@ class Bench:
         lib.vf_kernel_timing(0)
         kern_ms = kt.value / max(kn.value, 1)
         epi_ms = et.value / max(en.value, 1) if en.value else None
+        # a step that produced NaN / Inf is not a measurement: the trained grid is refined from the
+        # histogram of every timed iteration, so one non-finite event weight would show up here
+        if hasattr(inst, "divisions"):
+            g = inst.divisions
+            if not (bool(torch.isfinite(g).all()) and bool((g[:, 1:] >= g[:, :-1]).all())):
+                raise RuntimeError(f"workload {wl['name']}: the trained grid is not finite/monotone")
         clk = None
         if sampler:
             # keep the same steps running ~1 s more so the sampler sees the kernel under load
@@ -391,6 +397,25 @@ class Bench:
                     d2h=8 * inst._ROW + (final_grid.numel() * 8 / K if has_grid else 0))
 
 
+# fp64 operations per event of the IMPLEMENTED matrix-element chains (integrand only), counted by
+# compiling vf_integrands.cuh with an op-counting scalar (tests/host_shim/count_flops_host.cpp;
+# tests/test_device_source_on_host.py::test_implemented_chain_op_counts keeps these in sync).
+# `flops_per_event` / `frac` stay the ALGORITHMIC figure -- the reference chain's operations, like
+# 16d+9 for symgauss -- and the matrix-element kernels execute far fewer than that (exact-zero
+# parts of the spinor components, acos/sincos round trips and staged quotients are not formed):
+# the rows below carry both so that `frac` is not mistaken for pipe utilisation.
+IMPL_INTEGRAND_OPS = {"drellyan_lo": 128.0, "singletop_lo": 244.7}
+
+
+def impl_chain_fields(wl, t, peak):
+    ops = IMPL_INTEGRAND_OPS.get(wl["integrand"])
+    if ops is None:
+        return {}
+    f_impl = 12.0 * wl["n_dim"] + 5.0 + ops
+    return {"flops_per_event_implemented_chain": f_impl,
+            "frac_implemented_chain": t["achieved"] * f_impl / t["f_alg"] / peak}
+
+
 TABLE_1GPU = ["c1", "c2", "c3", "c4dy", "c4st", "c5", "sg8_rng32"]
 TABLE_NGPU = ["c2", "c3", "c5"]
 
@@ -442,6 +467,7 @@ def main():
                 "kernel_ms": t["kern_ms"], "epilogue_kernel_ms": t["epi_ms"],
                 "flops_per_event": t["f_alg"], "achieved_tflops": t["achieved"],
                 "frac": t["achieved"] / peak.value,
+                **impl_chain_fields(WORKLOADS[name], t, peak.value),
             }
 
     if rank == 0:
@@ -474,6 +500,7 @@ def main():
                                  "K-step pass run immediately after the timed region",
                 "kernel_share_of_step": m["kern_ms"] / (m["ms"] / K),
                 "epilogue_kernel_ms": m["epi_ms"],
+                **impl_chain_fields(wl, m, peak.value),
             },
             "clocks": m["clocks"],
             "e2e": {"value": e2e["value"], "unit": UNIT,

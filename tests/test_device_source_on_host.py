@@ -167,3 +167,97 @@ def test_matrix_elements_device_source(hs, golden, iid, name, d):
     if name == "drellyan_lo":
         closed = R.drellyan_closed_form(x2)
         assert np.median(np.abs(got - closed) / closed) < 2e-15
+
+
+def test_singletop_threshold_and_edge_regions(hs):
+    """single-top where the reference's own rounding is amplified (vf_integrands.cuh::angles_acos):
+    near threshold (x0 -> 0) the projected top momentum is anti-parallel to the beam and
+    cos(theta/2), sin(theta) carry the rounding of theta = rn(acos(c)); deep in that region
+    cos(phi) carries the rounding of phi = rn(acos(cx)) ~ pi/2.  The device source reproduces both
+    roundings without acos; the plain half-angle forms would leave 14 % of the first sample and
+    0.4 % of uniformly drawn points outside the bar."""
+    rng = np.random.default_rng(3)
+    n = 100000
+    for lo in (-8, -4, -2):
+        x = np.column_stack([10.0 ** rng.uniform(lo, 0, n), rng.random(n), rng.random(n)])
+        x = np.clip(x, R.TECH_CUT, 1 - R.TECH_CUT)
+        got, want = _integrand(hs, 3, x), R.INTEGRANDS["singletop_lo"](x)
+        rel = np.abs(got - want) / np.abs(want)
+        assert np.isfinite(got).all()
+        assert np.quantile(rel, 0.999) <= 1e-12 and (rel > 1e-12).mean() < 1e-3, lo
+    # both ends of x2 (cos of the scattering angle -> +-1) and of x1
+    ends = np.where(rng.random(n) < 0.5, 10.0 ** rng.uniform(-8, -1, n),
+                    1 - 10.0 ** rng.uniform(-8, -1, n))
+    for col in (1, 2):
+        x = rng.random((n, 3))
+        x[:, col] = ends
+        x = np.clip(x, R.TECH_CUT, 1 - R.TECH_CUT)
+        got, want = _integrand(hs, 3, x), R.INTEGRANDS["singletop_lo"](x)
+        rel = np.abs(got - want) / np.abs(want)
+        assert np.isfinite(got).all()
+        assert np.quantile(rel, 0.999) <= 1e-12 and (rel > 1e-12).mean() < 1e-3, col
+
+
+def test_drellyan_edge_regions(hs):
+    """Drell-Yan at the ends of every variable (x2 -> 1 makes Delta - 1 ill-conditioned: ptmax,
+    pta and Delta keep the reference's operations bit for bit there)."""
+    rng = np.random.default_rng(4)
+    n = 100000
+    ends = np.where(rng.random(n) < 0.5, 10.0 ** rng.uniform(-8, -1, n),
+                    1 - 10.0 ** rng.uniform(-8, -1, n))
+    for col in range(4):
+        x = rng.random((n, 4))
+        x[:, col] = ends
+        x = np.clip(x, R.TECH_CUT, 1 - R.TECH_CUT)
+        got, want = _integrand(hs, 2, x), R.INTEGRANDS["drellyan_lo"](x)
+        rel = np.abs(got - want) / np.abs(want)
+        assert np.isfinite(got).all()
+        assert np.quantile(rel, 0.99) <= 1e-12 and (rel > 1e-12).mean() < 5e-3, col
+
+
+def test_drellyan_tiny_kappa(hs):
+    """Drell-Yan grows like |ln kappa|/kappa, so a trained grid zooms in on kappa -> 0 iteration
+    after iteration and mV = sqrt(s kappa) runs through hundreds of binades.  The device source
+    collects its scalar quotients into one division on an exactly rescaled mV
+    (vf_integrands.cuh): finite and inside the bar wherever the reference is."""
+    rng = np.random.default_rng(5)
+    for ex in (-20, -60, -80, -120, -200, -290):
+        n = 2000
+        x = rng.random((n, 4))
+        x[:, 0] = 10.0 ** ex * (0.5 + rng.random(n))
+        got = _integrand(hs, 2, x)
+        with np.errstate(all="ignore"):
+            want = R.INTEGRANDS["drellyan_lo"](x)
+        assert np.isfinite(want).all() and np.isfinite(got).all(), ex
+        rel = np.abs(got - want) / np.abs(want)
+        assert np.quantile(rel, 0.99) <= 1e-12, ex
+
+
+def test_implemented_chain_op_counts():
+    """fp64 operations per event of the matrix-element chains AS IMPLEMENTED: vf_integrands.cuh
+    compiled with an op-counting scalar (tests/host_shim/count_flops_host.cpp; add/sub/mul/div/
+    sqrt/transcendental = 1, fma = 2).  bench.py reports them next to the algorithmic count of
+    the reference chain (vf_flops_per_event: 448 / 1354) so that `frac` is not read as pipe
+    utilisation."""
+    import bench
+
+    out = os.path.join(SHIM, "libcount_flops_host.so")
+    src = os.path.join(SHIM, "count_flops_host.cpp")
+    deps = [src, os.path.join(ROOT, "vegasflow_b200", "csrc", "vf_common.cuh"),
+            os.path.join(ROOT, "vegasflow_b200", "csrc", "vf_integrands.cuh")]
+    if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in deps):
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-I", SHIM, "-I",
+                               os.path.join(ROOT, "vegasflow_b200", "csrc"), "-I",
+                               os.path.join(ROOT, "include"), src, "-o", out])
+    lib = C.CDLL(out)
+    lib.hs_count_flops.restype = C.c_double
+    rng = np.random.default_rng(1)
+    for iid, name, d in ((2, "drellyan_lo", 4), (3, "singletop_lo", 3)):
+        x = R.TECH_CUT + rng.random((100000, d)) * (1 - 2 * R.TECH_CUT)
+        ops = lib.hs_count_flops(C.c_int(iid), C.c_int(d), C.c_long(x.shape[0]), _p(x),
+                                 C.c_double(0.0), C.c_double(0.0))
+        assert abs(ops - bench.IMPL_INTEGRAND_OPS[name]) <= 1.0, (name, ops)
+    # the counter itself: product of 8 numbers is 7 multiplications
+    x = rng.random((1000, 8))
+    assert lib.hs_count_flops(C.c_int(1), C.c_int(8), C.c_long(1000), _p(x), C.c_double(0.0),
+                              C.c_double(0.0)) == 7.0

@@ -120,9 +120,9 @@ def test_matrix_elements_on_a_large_random_grid(lib, name, d):
     """The matrix elements on 3e5 uniformly drawn points of a random grid (not only the golden
     vectors): bins / x / w bit-exact, w*f against the literal numpy restatement of the reference
     bodies at the SURVEY 7.4 bar -- 1e-12 for the bulk, < 0.5 % exceedance, aggregate 1e-12.
-    Drell-Yan is evaluated through half-angle forms (vf_integrands.cuh::angles_half): its
-    deviation from the literal route stays at the 1e-13 level; single-top keeps the literal
-    acos route because its threshold region needs the reference's own rounding of theta."""
+    Both are evaluated through half-angle forms (vf_integrands.cuh::angles_half, angles_acos);
+    single-top reproduces the reference's rounding of theta near pi and of phi near pi/2 where
+    its threshold region amplifies it (see test_singletop_threshold_region)."""
     n = 300000
     rng = np.random.default_rng(77 + d)
     r = R.TECH_CUT + rng.random((n, d)) * (1 - 2 * R.TECH_CUT)
@@ -142,6 +142,55 @@ def test_matrix_elements_on_a_large_random_grid(lib, name, d):
     assert np.quantile(rel, 0.99) <= REL_WF
     assert (rel > REL_WF).mean() < 5e-3
     assert abs(wf.sum() - det["wf"].sum()) <= REL_WF * np.abs(det["wf"]).sum()
+
+
+def test_drellyan_on_a_grid_zoomed_in_on_small_kappa(lib):
+    """Drell-Yan grows like |ln kappa|/kappa: training zooms the first dimension in on kappa -> 0
+    without end, and mV = sqrt(s kappa) runs through hundreds of binades.  A grid
+    whose first bins end at 1e-280 ... 1e-20: the kernel stays finite and inside the bar
+    wherever the reference is (its collected quotient is evaluated on an exactly rescaled mV)."""
+    n, d = 100000, 4
+    rng = np.random.default_rng(91)
+    r = R.TECH_CUT + rng.random((n, d)) * (1 - 2 * R.TECH_CUT)
+    grid = R.initial_divisions(d)
+    small = 10.0 ** np.array([-280, -240, -200, -160, -120, -80, -60, -40, -20, -10], dtype=float)
+    grid[0, 1:11] = small
+    grid[0, 11:] = np.linspace(0.01, 1.0, 40)
+    iid = lib.vf_integrand_id(b"drellyan_lo")
+    x, w, ind, wf = gpu_digest(lib, 1, iid, r, grid, 1.0 / n)
+    _, _, _, det = R.vegas_run_event(r, grid, R.INTEGRANDS["drellyan_lo"], n, train=False)
+    np.testing.assert_array_equal(ind, det["ind"])
+    np.testing.assert_array_equal(x, det["x"])
+    np.testing.assert_array_equal(w, det["w"])
+    assert (x[:, 0] < 1e-100).mean() > 0.05
+    assert np.isfinite(det["wf"]).all() and np.isfinite(wf).all()
+    rel = np.abs(wf - det["wf"]) / np.abs(det["wf"])
+    assert np.quantile(rel, 0.99) <= REL_WF and (rel > REL_WF).mean() < 5e-3
+
+
+@pytest.mark.parametrize("lo", [-8, -4, -2])
+def test_singletop_threshold_region(lib, lo):
+    """single-top with x0 drawn log-uniformly down to TECH_CUT: near threshold the projected top
+    momentum is anti-parallel to the beam, and the reference's cos(theta/2), sin(theta), cos(phi)
+    carry the rounding of theta = rn(acos(c)) and phi = rn(acos(cx)) as relative errors up to 1e-8.
+    The kernel reproduces those roundings in IEEE add/multiply/divide/sqrt arithmetic (no acos):
+    99.9 % of the events inside 1e-12 here too."""
+    n, d = 100000, 3
+    rng = np.random.default_rng(300 - lo)
+    x0 = 10.0 ** rng.uniform(lo, 0, n)
+    r = np.column_stack([x0, rng.random(n), rng.random(n)])
+    r = np.clip(r, R.TECH_CUT, 1 - R.TECH_CUT)
+    # flat grid and the digest's flip (x = 1 - r on the uniform grid up to rounding): feed 1 - x
+    grid = R.initial_divisions(d)
+    iid = lib.vf_integrand_id(b"singletop_lo")
+    x, w, ind, wf = gpu_digest(lib, 1, iid, 1.0 - r, grid, 1.0 / n)
+    want = R.INTEGRANDS["singletop_lo"](x) * w
+    assert np.isfinite(wf).all()
+    assert (x[:, 0] < 10.0 ** (lo / 2)).mean() > 0.3  # the sample does reach the region
+    rel = np.abs(wf - want) / np.abs(want)
+    print(f"singletop threshold 1e{lo}: q99 {np.quantile(rel, 0.99):.2e} "
+          f"q999 {np.quantile(rel, 0.999):.2e} exceed {(rel > REL_WF).mean():.2e}")
+    assert np.quantile(rel, 0.999) <= REL_WF and (rel > REL_WF).mean() < 1e-3
 
 
 @pytest.mark.parametrize("name,d,n", [("symgauss", 4, 200000), ("symgauss", 8, 100000),
