@@ -11,33 +11,78 @@
 namespace vf {
 
 // Launch configuration per (dimension count, register class).  Shared memory per block:
-//   table  NDIM*50*TC*16 B  (x_ini, Delta) pairs, TC lane-interleaved copies
-//   hist   NDIM*50*HC*8  B  histogram, HC lane-interleaved copies
-// Interleaving by (lane % copies) keeps the LDS.128 table reads and the 64-bit histogram
-// updates bank-conflict free for any bin pattern (TC >= 8, HC >= 16).
+//   table   NDIM*50*TC*16 B    (x_ini, Delta) pairs, TC lane-interleaved copies
+//   pairs   NP*50*50*JC*8 B    one 50x50 histogram per PAIR of dimensions (2p, 2p+1), JC copies
+//   singles (NDIM-2NP)*50*HC*8 B  one 50-bin histogram per remaining dimension, HC copies
+// Interleaving by (lane % copies) keeps the LDS.128 table reads and the 64-bit updates of the
+// single histograms bank-conflict free for any bin pattern (TC >= 8, HC >= 16).
+//
+// PAIR HISTOGRAMS.  The reference fills one histogram per dimension with (w f)^2 (vflow.py:
+// 370-387); every update is a shared-memory read-modify-write loop (load, DADD, ATOMS.CAST.SPIN,
+// branch: sm_100 has no native shared fp64 add), seven instructions per dimension per event.  A
+// 50x50 histogram over the bin PAIR of two dimensions takes ONE update for both, and its row and
+// column sums -- taken once per launch, in a fixed order -- are exactly the two per-dimension
+// histograms (sums of non-negative terms: the different summation order is ~1e-16 relative).
+// Half the updates: -4.1 % kernel time at d = 8, -5.8 % at d = 4, -7.4 % at d = 10
+// (profiles/r2_k1_pairs.txt), although the 2500-cell histograms are hit with bank conflicts
+// (random cells) and leave room for one or two copies only.  Used for light integrands with
+// d <= 10, d = 12 and d = 14 (choose_smem); the remaining dimension of an odd n_dim, every
+// dimension of the other shapes and of the heavy integrands keep per-dimension histograms.
+//
 // ONE block per SM for every shape; measured on B200 (profiles/r2_k1_variants.txt):
 //   * 1024 threads with the 64-register budget beat 512 threads with 128 registers for every
 //     light integrand (-10 % at d = 9 ... 16; -2 % against two 512-thread blocks at d <= 8);
 //     768 threads (85 registers) are 3 % better at d >= 19, where 64 registers spill too much;
-//   * histogram copies are what the shared-memory atomics need most: HC = 32 (one copy per
-//     lane, no same-address collisions inside a warp) wherever it fits, else 16; the table gets
-//     what is left of the 227 KB (TC = 16 up to d = 8, 8 up to d = 12 and d = 15 ... 18, else 4);
+//   * per-dimension histograms: copies are what the shared-memory atomics need most, HC = 32 (one
+//     copy per lane, no same-address collisions inside a warp) wherever it fits, else 16;
 //   * heavy integrands keep 512 threads and the 128-register budget unless they name a block
-//     size themselves (`kBlockThreads`: Drell-Yan runs 768 x 80 registers, +12 %).
+//     size themselves (`kBlockThreads`).
 constexpr size_t kSmemBudget = 227 * 1024 - 2048;  // opt-in limit minus static + reserved
-constexpr size_t cfg_smem_bytes(int n_dim, int tc, int hc) {
-    return (size_t)n_dim * kBins * (16 * tc + 8 * hc);
+struct SmemChoice {
+    int np, jc, tc, hc;  // dimension pairs, copies of a pair histogram, table copies, single copies
+};
+constexpr size_t cfg_smem_bytes(int n_dim, SmemChoice c) {
+    return (size_t)n_dim * kBins * 16 * c.tc + (size_t)c.np * kBins * kBins * 8 * c.jc +
+           (size_t)(n_dim - 2 * c.np) * kBins * 8 * c.hc;
+}
+constexpr SmemChoice choose_smem(int n_dim, bool heavy) {
+#if defined(VF_EXP_NP)  // experiment harness: force a layout
+    return SmemChoice{VF_EXP_NP < 0 ? n_dim / 2 : VF_EXP_NP, VF_EXP_JC, VF_EXP_TC, VF_EXP_HC};
+#else
+#ifndef VF_EXP_NOPAIRS
+    // measured, d = 2 ... 20 (profiles/r2_k1_pairs.txt): pairs pay with two copies, or with one
+    // copy where they free the shared memory for a 16-copy table (d = 10) or at least keep 8
+    // (d = 12, 14); odd d gain < 1 %, d = 11 and 13 lose 1-5 %, and from d = 15 on the pairs would
+    // squeeze the table to 4 copies (+16 ... 23 %), as does any partial pairing at d = 16 ... 20
+    if (!heavy && n_dim >= 2 && (n_dim <= 10 || n_dim == 12 || n_dim == 14)) {
+        const int np = n_dim / 2;
+        const SmemChoice cands[] = {{np, 2, 16, 32}, {np, 2, 8, 32}, {np, 1, 16, 32}, {np, 1, 8, 32}};
+        for (const SmemChoice& c : cands)
+            if (cfg_smem_bytes(n_dim, c) <= kSmemBudget) return c;
+    }
+#endif
+    // one histogram per dimension; the table gets what is left of the 227 KB (TC = 16 up to
+    // d = 8, 8 up to d = 12 and d = 15 ... 18, else 4)
+    const int hc = cfg_smem_bytes(n_dim, SmemChoice{0, 0, 4, 32}) <= kSmemBudget ? 32 : 16;
+    const int tc = (n_dim <= 8 && cfg_smem_bytes(n_dim, SmemChoice{0, 0, 16, hc}) <= kSmemBudget)
+                       ? 16
+                       : (cfg_smem_bytes(n_dim, SmemChoice{0, 0, 8, hc}) <= kSmemBudget ? 8 : 4);
+    return SmemChoice{0, 1, tc, hc};
+#endif
 }
 template <int NDIM, bool HEAVY, int THREADS = 0>
 struct CfgT {
     static constexpr int kThreads = THREADS ? THREADS : (HEAVY ? 512 : (NDIM >= 19 ? 768 : 1024));
-    static constexpr int HC = cfg_smem_bytes(NDIM, 4, 32) <= kSmemBudget ? 32 : 16;
-    static constexpr int TC = (NDIM <= 8 && cfg_smem_bytes(NDIM, 16, HC) <= kSmemBudget)
-                                  ? 16
-                                  : (cfg_smem_bytes(NDIM, 8, HC) <= kSmemBudget ? 8 : 4);
+    static constexpr SmemChoice kChoice = choose_smem(NDIM, HEAVY);
+    static constexpr int NP = kChoice.np;        // dimensions 0 ... 2NP-1 are paired
+    static constexpr int JC = kChoice.jc;
+    static constexpr int TC = kChoice.tc;
+    static constexpr int HC = kChoice.hc;
+    static constexpr int kSingles = NDIM - 2 * NP;
     static constexpr int kTblEntries = NDIM * kBins * TC;
-    static constexpr int kHistEntries = NDIM * kBins * HC;
-    static constexpr size_t kSmemBytes = cfg_smem_bytes(NDIM, TC, HC);
+    static constexpr int kPairEntries = NP * kBins * kBins * JC;
+    static constexpr int kHistEntries = kPairEntries + kSingles * kBins * HC;
+    static constexpr size_t kSmemBytes = cfg_smem_bytes(NDIM, kChoice);
     static_assert(kSmemBytes <= kSmemBudget, "n_dim too large for the fused kernels");
 };
 // an integrand may fix its block size with `static constexpr int kBlockThreads`
@@ -120,13 +165,40 @@ __device__ __forceinline__ void write_partials(double sum, double sum2, const do
     }
     if (with_hist) {
         double* acc = workspace + ws_acc_offset();
-        for (int i = threadIdx.x; i < NDIM * kBins; i += blockDim.x) {
+        // paired dimensions: row / column sums of the pair histograms.  Four lanes share one
+        // (dimension, bin): lane q adds the cells k = q, q+4, ... of every copy, the quad is
+        // folded with two shuffles (a fixed order), its first lane issues the RED.  The loop
+        // bound is warp-uniform so that every lane reaches the shuffles.
+        constexpr int kPairTasks = 2 * C::NP * kBins * 4;
+        for (int t0 = (threadIdx.x & ~31); t0 < kPairTasks; t0 += blockDim.x) {
+            const int t = t0 + lane;
+            double part = 0.0;
+            const int i = t >> 2, q = t & 3;
+            if (t < kPairTasks) {
+                const int j = i / kBins, b = i - j * kBins;
+                const double* h = hist + (size_t)(j >> 1) * (kBins * kBins * C::JC);
+                const int first = (j & 1) ? b : b * kBins, step = (j & 1) ? kBins : 1;
+                for (int k = q; k < kBins; k += 4) {
+                    int kk = k + b;  // rotate the start: neighbouring quads read different banks
+                    if (kk >= kBins) kk -= kBins;
+                    const double* cell = h + (first + kk * step) * C::JC;
+#pragma unroll
+                    for (int c = 0; c < C::JC; ++c) part += cell[c];
+                }
+            }
+            part += __shfl_xor_sync(0xffffffffu, part, 1);
+            part += __shfl_xor_sync(0xffffffffu, part, 2);
+            if (q == 0 && t < kPairTasks) atomicAdd(acc + i, part);  // RED.E.ADD.F64
+        }
+        // single dimensions: reduce the HC copies
+        const double* hs = hist + C::kPairEntries;
+        for (int i = threadIdx.x; i < C::kSingles * kBins; i += blockDim.x) {
             double t = 0.0;
             // thread i starts at copy i: the lanes of a warp read different banks (a plain
             // c = 0.. walk has all 32 lanes on one bank: the rows are HC*8 = 256 B apart)
 #pragma unroll
-            for (int c = 0; c < C::HC; ++c) t += hist[i * C::HC + ((c + i) & (C::HC - 1))];
-            atomicAdd(acc + i, t);  // RED.E.ADD.F64
+            for (int c = 0; c < C::HC; ++c) t += hs[i * C::HC + ((c + i) & (C::HC - 1))];
+            atomicAdd(acc + 2 * C::NP * kBins + i, t);  // RED.E.ADD.F64
         }
     }
 }
@@ -139,20 +211,23 @@ __device__ __forceinline__ void write_partials(double sum, double sum2, const do
 // half-warps on disjoint dimensions, one dimension at a time, 32 copies
 // (profiles/r2_k1_variants.txt): ~5.7 CAS retries per warp-event happen either way and the cost
 // is the instruction count.
-// `row[j]` is the shared-window address of the event's TABLE row in dimension j when the table
-// and histogram row pitches agree (then the histogram cell is row + a per-lane constant, one
-// IADD3), else of its histogram row; the dimension offset folds into the address immediate.
+// What the event loop keeps per dimension until the update (`keep`): the BIN for a paired
+// dimension; for a single dimension the shared-window address of the event's TABLE row when the
+// table and histogram row pitches agree and nothing is paired (then the histogram cell is row + a
+// per-lane constant, one IADD3), else of its histogram row.  Dimension offsets fold into the
+// address immediates.
 template <class C>
 struct HistAddr {
-    static constexpr bool kSamePitch = (C::TC * 16 == C::HC * 8);
-    uint32_t tbl_s, hist_s, delta;
+    static constexpr bool kSamePitch = (C::NP == 0) && (C::TC * 16 == C::HC * 8);
+    uint32_t tbl_s, pair_s, hist_s, delta;
     __device__ __forceinline__ HistAddr(const void* tbl, const void* hist, int lane) {
         tbl_s = smem_u32(tbl) + (uint32_t)(lane % C::TC) * 16u;
-        hist_s = smem_u32(hist) + (uint32_t)(lane % C::HC) * 8u;
+        pair_s = smem_u32(hist) + (uint32_t)(lane % C::JC) * 8u;
+        hist_s = smem_u32(hist) + (uint32_t)C::kPairEntries * 8u + (uint32_t)(lane % C::HC) * 8u;
         delta = hist_s - tbl_s;
     }
-    // what to keep per dimension until the histogram update
-    __device__ __forceinline__ uint32_t keep(int bin, uint32_t tbl_row) const {
+    __device__ __forceinline__ uint32_t keep(int j, int bin, uint32_t tbl_row) const {
+        if (j < 2 * C::NP) return (uint32_t)bin;
         return kSamePitch ? tbl_row : row_addr<C::HC * 8>(bin, hist_s);
     }
 };
@@ -160,9 +235,15 @@ template <class C, int NDIM>
 __device__ __forceinline__ void hist_update(const HistAddr<C>& ha, const uint32_t (&row)[NDIM],
                                             double tmp2) {
 #pragma unroll
-    for (int j = 0; j < NDIM; ++j)
+    for (int p = 0; p < C::NP; ++p) {  // one update for dimensions 2p and 2p+1
+        const uint32_t cell = row[2 * p] * (uint32_t)kBins + row[2 * p + 1];
+        red_shared_f64(cell * (uint32_t)(C::JC * 8) + ha.pair_s,
+                       (uint32_t)p * (kBins * kBins * C::JC * 8), tmp2);
+    }
+#pragma unroll
+    for (int j = 2 * C::NP; j < NDIM; ++j)
         red_shared_f64(HistAddr<C>::kSamePitch ? row[j] + ha.delta : row[j],
-                       (uint32_t)j * (kBins * C::HC * 8), tmp2);
+                       (uint32_t)(j - 2 * C::NP) * (kBins * C::HC * 8), tmp2);
 }
 
 // ---------------------------------------------------------------------------
@@ -220,7 +301,7 @@ event_kernel(const __grid_constant__ EventKernelArgs a) {
                         vegas_map_dim_s<C::TC>(xn, ha.tbl_s,
                                                (uint32_t)j * (kBins * C::TC * 16),
                                                x[j], wfac, bin, trow);
-                        row[j] = ha.keep(bin, trow);
+                        row[j] = ha.keep(j, bin, trow);
                         w = (j == 0) ? wfac : __dmul_rn(w, wfac);  // reduce_prod, vflow.py:78
                     } else {
                         x[j] = __dsub_rn(2.0, v);  // r itself, monte_carlo.py:290-298
@@ -439,7 +520,7 @@ plus_event_kernel(const __grid_constant__ PlusKernelArgs a) {
                     vegas_map_dim_s<C::TC>(xn, ha.tbl_s,
                                            (uint32_t)j * (kBins * C::TC * 16), x[j],
                                            wfac, bin[j], trow);
-                    row[j] = ha.keep(bin[j], trow);
+                    row[j] = ha.keep(j, bin[j], trow);
                     w = (j == 0) ? wfac : __dmul_rn(w, wfac);
                 }
             }
