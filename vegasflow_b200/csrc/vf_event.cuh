@@ -96,6 +96,22 @@ struct BlockThreadsOf<I, std::void_t<decltype(I::kBlockThreads)>> {
 };
 template <class I, int NDIM>
 using Cfg = CfgT<NDIM, I::kHeavy, BlockThreadsOf<I>::value>;
+// The VEGAS+ kernel carries the cube coordinates and per-cube divisors on top of the event
+// kernel's state (64 registers spill 56 B at d = 8, 120 B at d = 10): it takes a block size of its
+// own, measured on uniform allocations of 5e7 events (profiles/r2_plus_variants.txt): 640 threads
+// (84 ... 96 registers) -9 % at d = 4, -4 % at d = 8 and d = 12; 768 threads -2 % at d = 6; the
+// event kernel's 1024 at d = 10.  VF_PLUS_THREADS overrides (experiment harness).
+constexpr int plus_threads(int n_dim) {
+#ifdef VF_PLUS_THREADS
+    return VF_PLUS_THREADS;
+#else
+    return n_dim <= 4 ? 640 : (n_dim <= 7 ? 768 : (n_dim <= 9 || n_dim == 12 ? 640 : 0));
+#endif
+}
+template <class I, int NDIM>
+using PlusCfg = CfgT<NDIM, I::kHeavy,
+                     BlockThreadsOf<I>::value ? BlockThreadsOf<I>::value
+                                              : (I::kHeavy ? 0 : plus_threads(NDIM))>;
 
 struct EventKernelArgs {
     const double* divisions;  // [NDIM][51]
@@ -416,9 +432,9 @@ struct PlusKernelArgs {
 };
 
 template <class I, int NDIM, bool EXT, int RB>
-__global__ void __launch_bounds__(Cfg<I, NDIM>::kThreads, 1)
+__global__ void __launch_bounds__(PlusCfg<I, NDIM>::kThreads, 1)
 plus_event_kernel(const __grid_constant__ PlusKernelArgs a) {
-    using C = Cfg<I, NDIM>;
+    using C = PlusCfg<I, NDIM>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double2* tbl = reinterpret_cast<double2*>(smem_raw);
     double* hist = reinterpret_cast<double*>(smem_raw + (size_t)C::kTblEntries * 16);
@@ -644,7 +660,7 @@ int launch_digest_dim(const DigestLaunch& L) {
 
 template <class I, int NDIM>
 int launch_plus_dim(const PlusLaunch& L) {
-    using C = Cfg<I, NDIM>;
+    using C = PlusCfg<I, NDIM>;
     const bool ext = L.k.rnds != nullptr;
     auto kern = ext ? plus_event_kernel<I, NDIM, true, 52>
                     : (L.rng_bits == 32 ? plus_event_kernel<I, NDIM, false, 32>
