@@ -29,10 +29,13 @@ namespace vf {
 // d <= 10, d = 12 and d = 14 (choose_smem); the remaining dimension of an odd n_dim, every
 // dimension of the other shapes and of the heavy integrands keep per-dimension histograms.
 //
-// ONE block per SM for every shape; measured on B200 (profiles/r2_k1_variants.txt):
+// ONE block per SM for every shape; measured on B200 (profiles/r2_k1_variants.txt,
+// r2_k1_threads.txt):
 //   * 1024 threads with the 64-register budget beat 512 threads with 128 registers for every
-//     light integrand (-10 % at d = 9 ... 16; -2 % against two 512-thread blocks at d <= 8);
-//     768 threads (85 registers) are 3 % better at d >= 19, where 64 registers spill too much;
+//     light integrand (-10 % at d = 9 ... 16; -2 % against two 512-thread blocks at d <= 8) and,
+//     since the kernels got leaner (62 registers, no spill even at d = 20), 768 threads at
+//     d = 19, 20 as well (-6 %, -9 %); 896 threads (72 registers) win at d = 10, 12, 13, 16
+//     (-5, -2.7, -1.5, -1.8 %);
 //   * per-dimension histograms: copies are what the shared-memory atomics need most, HC = 32 (one
 //     copy per lane, no same-address collisions inside a warp) wherever it fits, else 16;
 //   * heavy integrands keep 512 threads and the 128-register budget unless they name a block
@@ -56,6 +59,10 @@ constexpr SmemChoice choose_smem(int n_dim, bool heavy) {
     // squeeze the table to 4 copies (+16 ... 23 %), as does any partial pairing at d = 16 ... 20
     if (!heavy && n_dim >= 2 && (n_dim <= 10 || n_dim == 12 || n_dim == 14)) {
         const int np = n_dim / 2;
+        // d = 4: an 8-copy table is as fast as 16 copies (0.934 vs 0.949 ms per 1e8 events) and
+        // keeps the block at 106 KB: two blocks fit one SM, so the next iteration's event kernel
+        // (programmatic dependent launch) can get resident beside the running one
+        if (n_dim == 4) return SmemChoice{np, 2, 8, 32};
         const SmemChoice cands[] = {{np, 2, 16, 32}, {np, 2, 8, 32}, {np, 1, 16, 32}, {np, 1, 8, 32}};
         for (const SmemChoice& c : cands)
             if (cfg_smem_bytes(n_dim, c) <= kSmemBudget) return c;
@@ -72,7 +79,13 @@ constexpr SmemChoice choose_smem(int n_dim, bool heavy) {
 }
 template <int NDIM, bool HEAVY, int THREADS = 0>
 struct CfgT {
-    static constexpr int kThreads = THREADS ? THREADS : (HEAVY ? 512 : (NDIM >= 19 ? 768 : 1024));
+#ifdef VF_EXP_EVENT_THREADS  // experiment harness: force the block size of the light kernels
+    static constexpr int kThreads = THREADS ? THREADS : (HEAVY ? 512 : VF_EXP_EVENT_THREADS);
+#else
+    static constexpr int kThreads =
+        THREADS ? THREADS
+                : (HEAVY ? 512 : ((NDIM == 10 || NDIM == 12 || NDIM == 13 || NDIM == 16) ? 896 : 1024));
+#endif
     static constexpr SmemChoice kChoice = choose_smem(NDIM, HEAVY);
     static constexpr int NP = kChoice.np;        // dimensions 0 ... 2NP-1 are paired
     static constexpr int JC = kChoice.jc;
@@ -100,12 +113,14 @@ using Cfg = CfgT<NDIM, I::kHeavy, BlockThreadsOf<I>::value>;
 // kernel's state (64 registers spill 56 B at d = 8, 120 B at d = 10): it takes a block size of its
 // own, measured on uniform allocations of 5e7 events (profiles/r2_plus_variants.txt): 640 threads
 // (84 ... 96 registers) -9 % at d = 4, -4 % at d = 8 and d = 12; 768 threads -2 % at d = 6; the
-// event kernel's 1024 at d = 10.  VF_PLUS_THREADS overrides (experiment harness).
+// event kernel's block size at d = 10 ... 16; 768 threads from d = 17 on, where 64 registers would
+// spill hundreds of bytes.  VF_PLUS_THREADS overrides (experiment harness).
 constexpr int plus_threads(int n_dim) {
 #ifdef VF_PLUS_THREADS
     return VF_PLUS_THREADS;
 #else
-    return n_dim <= 4 ? 640 : (n_dim <= 7 ? 768 : (n_dim <= 9 || n_dim == 12 ? 640 : 0));
+    return n_dim <= 4 ? 640
+                      : (n_dim <= 7 ? 768 : (n_dim <= 9 || n_dim == 12 ? 640 : (n_dim >= 17 ? 768 : 0)));
 #endif
 }
 template <class I, int NDIM>
