@@ -35,7 +35,7 @@ namespace vf {
 //     light integrand (-10 % at d = 9 ... 16; -2 % against two 512-thread blocks at d <= 8) and,
 //     since the kernels got leaner (62 registers, no spill even at d = 20), 768 threads at
 //     d = 19, 20 as well (-6 %, -9 %); 896 threads (72 registers) win at d = 10, 12, 13, 16
-//     (-5, -2.7, -1.5, -1.8 %);
+//     (-5, -2.7, -1.5, -1.8 %) and are the unmeasured default beyond d = 20 (user integrands);
 //   * per-dimension histograms: copies are what the shared-memory atomics need most, HC = 32 (one
 //     copy per lane, no same-address collisions inside a warp) wherever it fits, else 16;
 //   * heavy integrands keep 512 threads and the 128-register budget unless they name a block
@@ -84,7 +84,9 @@ struct CfgT {
 #else
     static constexpr int kThreads =
         THREADS ? THREADS
-                : (HEAVY ? 512 : ((NDIM == 10 || NDIM == 12 || NDIM == 13 || NDIM == 16) ? 896 : 1024));
+                : (HEAVY ? 512
+                         : ((NDIM == 10 || NDIM == 12 || NDIM == 13 || NDIM == 16 || NDIM > 20) ? 896
+                                                                                                : 1024));
 #endif
     static constexpr SmemChoice kChoice = choose_smem(NDIM, HEAVY);
     static constexpr int NP = kChoice.np;        // dimensions 0 ... 2NP-1 are paired

@@ -19,7 +19,8 @@ import subprocess
 
 import torch
 
-# largest n_dim whose fused-kernel shared memory (n_dim * 9600 B) fits the 227 KB opt-in limit
+# largest n_dim whose fused-kernel shared memory (vf_event.cuh::choose_smem: 4 table copies and
+# 16 histogram copies, n_dim * 9600 B, at the top end) fits the 227 KB opt-in limit
 MAX_FUSED_DIM = 24
 
 
