@@ -234,12 +234,11 @@ def test_drellyan_tiny_kappa(hs):
 
 
 def test_implemented_chain_op_counts():
-    """fp64 operations per event of the matrix-element chains AS IMPLEMENTED: vf_integrands.cuh
-    compiled with an op-counting scalar (tests/host_shim/count_flops_host.cpp; add/sub/mul/div/
-    sqrt/transcendental = 1, fma = 2).  bench.py reports them next to the algorithmic count of
-    the reference chain (vf_flops_per_event: 448 / 1354) so that `frac` is not read as pipe
-    utilisation."""
-    import bench
+    """F_alg of the matrix elements as SURVEY 8(d) prescribes: vf_integrands.cuh compiled with an
+    op-counting scalar (tests/host_shim/count_flops_host.cpp; add/sub/mul/div/sqrt/
+    transcendental = 1, fma = 2), averaged over uniformly drawn events, must be what
+    vf_flops_per_event returns on top of the 12d+5 of the VEGAS step."""
+    from vegasflow_b200 import _lib
 
     out = os.path.join(SHIM, "libcount_flops_host.so")
     src = os.path.join(SHIM, "count_flops_host.cpp")
@@ -251,12 +250,14 @@ def test_implemented_chain_op_counts():
                                os.path.join(ROOT, "include"), src, "-o", out])
     lib = C.CDLL(out)
     lib.hs_count_flops.restype = C.c_double
+    abi = _lib.load()
     rng = np.random.default_rng(1)
     for iid, name, d in ((2, "drellyan_lo", 4), (3, "singletop_lo", 3)):
         x = R.TECH_CUT + rng.random((100000, d)) * (1 - 2 * R.TECH_CUT)
         ops = lib.hs_count_flops(C.c_int(iid), C.c_int(d), C.c_long(x.shape[0]), _p(x),
                                  C.c_double(0.0), C.c_double(0.0))
-        assert abs(ops - bench.IMPL_INTEGRAND_OPS[name]) <= 1.0, (name, ops)
+        table = abi.vf_flops_per_event(1, abi.vf_integrand_id(name.encode()), d, 0) - (12 * d + 5)
+        assert abs(ops - table) <= 1.0, (name, ops, table)
     # the counter itself: product of 8 numbers is 7 multiplications
     x = rng.random((1000, 8))
     assert lib.hs_count_flops(C.c_int(1), C.c_int(8), C.c_long(1000), _p(x), C.c_double(0.0),
