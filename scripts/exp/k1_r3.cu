@@ -1,7 +1,9 @@
 // Experiment harness (not product code), round 2: times the PRODUCT event kernel
 // (vegasflow_b200/csrc/vf_event.cuh) standalone on 1e8 events.  The -DVF_EXP_* switches that
 // selected the recorded variants (profiles/r2_k1_r3_*.txt) lived in the product headers up to commit
-// "Experiments on the product event kernel: per-warp loop-exit clocks ..." and were removed after:
+// "Experiments on the product event kernel: per-warp loop-exit clocks ..." and were removed after;
+// the session-3 switches (VF_EXP_NP / _JC / _TC / _HC, VF_EXP_NOPAIRS, VF_EXP_EVENT_THREADS, VF_EXP_MAD_ADDR:
+// profiles/r2_k1_pairs.txt, r2_k1_threads.txt) lived there up to commit 9142b36:
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -fmad=false -std=c++17 -I include
 //        -I vegasflow_b200/csrc [-DVF_EXP_...] scripts/exp/k1_r3.cu -o scripts/exp/k1_r3_<variant>
 // Prints best-of-5 kernel time, events/s and checksums (sum wf, sum wf^2, sum of the histogram) so

@@ -1,7 +1,8 @@
 // Experiment harness (not product code), round 2 session 3: times the PRODUCT VEGAS+ event kernel
 // (vegasflow_b200/csrc/vf_event.cuh::plus_event_kernel) standalone on a uniform sample allocation
 // (n_strat^d cubes, the same event count in every cube), like scripts/exp/k1_r3.cu does for the
-// event kernel.  Build-time switches: -DEXP_DIM, -DVF_PLUS_THREADS, -DVF_EXP_NOPAIRS, ...
+// event kernel.  Build-time switches: -DEXP_DIM, -DEXP_STRAT; the product-header switches of the recorded
+// variants (-DVF_PLUS_THREADS, -DVF_EXP_NOPAIRS: profiles/r2_plus_variants.txt) lived there up to commit 9142b36.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -fmad=false -std=c++17 -I include
 //        -I vegasflow_b200/csrc [-D...] scripts/exp/plus_r3.cu -o scripts/exp/plus_r3_<variant>
 #include <cmath>

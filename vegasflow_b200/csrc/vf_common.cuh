@@ -249,13 +249,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 template <int PITCH>
 __device__ __forceinline__ uint32_t row_addr(int bin, uint32_t base) {
-#ifdef VF_EXP_MAD_ADDR
-    uint32_t r;
-    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(bin), "n"(PITCH), "r"(base));
-    return r;
-#else
+    // a plain C expression: ptxas schedules it better than an inline mad.lo.u32 (-1.2 % at d = 8,
+    // profiles/r2_k1_pairs.txt)
     return base + (uint32_t)bin * (uint32_t)PITCH;
-#endif
 }
 // `off` is a compile-time constant after unrolling: ptxas folds it into the address immediate
 __device__ __forceinline__ double2 lds_f64x2(uint32_t addr, uint32_t off) {

@@ -49,10 +49,6 @@ constexpr size_t cfg_smem_bytes(int n_dim, SmemChoice c) {
            (size_t)(n_dim - 2 * c.np) * kBins * 8 * c.hc;
 }
 constexpr SmemChoice choose_smem(int n_dim, bool heavy) {
-#if defined(VF_EXP_NP)  // experiment harness: force a layout
-    return SmemChoice{VF_EXP_NP < 0 ? n_dim / 2 : VF_EXP_NP, VF_EXP_JC, VF_EXP_TC, VF_EXP_HC};
-#else
-#ifndef VF_EXP_NOPAIRS
     // measured, d = 2 ... 20 (profiles/r2_k1_pairs.txt): pairs pay with two copies, or with one
     // copy where they free the shared memory for a 16-copy table (d = 10) or at least keep 8
     // (d = 12, 14); odd d gain < 1 %, d = 11 and 13 lose 1-5 %, and from d = 15 on the pairs would
@@ -67,7 +63,6 @@ constexpr SmemChoice choose_smem(int n_dim, bool heavy) {
         for (const SmemChoice& c : cands)
             if (cfg_smem_bytes(n_dim, c) <= kSmemBudget) return c;
     }
-#endif
     // one histogram per dimension; the table gets what is left of the 227 KB (TC = 16 up to
     // d = 8, 8 up to d = 12 and d = 15 ... 18, else 4)
     const int hc = cfg_smem_bytes(n_dim, SmemChoice{0, 0, 4, 32}) <= kSmemBudget ? 32 : 16;
@@ -75,19 +70,14 @@ constexpr SmemChoice choose_smem(int n_dim, bool heavy) {
                        ? 16
                        : (cfg_smem_bytes(n_dim, SmemChoice{0, 0, 8, hc}) <= kSmemBudget ? 8 : 4);
     return SmemChoice{0, 1, tc, hc};
-#endif
 }
 template <int NDIM, bool HEAVY, int THREADS = 0>
 struct CfgT {
-#ifdef VF_EXP_EVENT_THREADS  // experiment harness: force the block size of the light kernels
-    static constexpr int kThreads = THREADS ? THREADS : (HEAVY ? 512 : VF_EXP_EVENT_THREADS);
-#else
     static constexpr int kThreads =
         THREADS ? THREADS
                 : (HEAVY ? 512
                          : ((NDIM == 10 || NDIM == 12 || NDIM == 13 || NDIM == 16 || NDIM > 20) ? 896
                                                                                                 : 1024));
-#endif
     static constexpr SmemChoice kChoice = choose_smem(NDIM, HEAVY);
     static constexpr int NP = kChoice.np;        // dimensions 0 ... 2NP-1 are paired
     static constexpr int JC = kChoice.jc;
@@ -116,14 +106,10 @@ using Cfg = CfgT<NDIM, I::kHeavy, BlockThreadsOf<I>::value>;
 // own, measured on uniform allocations of 5e7 events (profiles/r2_plus_variants.txt): 640 threads
 // (84 ... 96 registers) -9 % at d = 4, -4 % at d = 8 and d = 12; 768 threads -2 % at d = 6; the
 // event kernel's block size at d = 10 ... 16; 768 threads from d = 17 on, where 64 registers would
-// spill hundreds of bytes.  VF_PLUS_THREADS overrides (experiment harness).
+// spill hundreds of bytes.
 constexpr int plus_threads(int n_dim) {
-#ifdef VF_PLUS_THREADS
-    return VF_PLUS_THREADS;
-#else
     return n_dim <= 4 ? 640
                       : (n_dim <= 7 ? 768 : (n_dim <= 9 || n_dim == 12 ? 640 : (n_dim >= 17 ? 768 : 0)));
-#endif
 }
 template <class I, int NDIM>
 using PlusCfg = CfgT<NDIM, I::kHeavy,
