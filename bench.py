@@ -307,22 +307,29 @@ class Bench:
         step_s = self.agree_max((time.perf_counter() - t0) / W)
         self.run_steps(inst, int(min(2000, max(0, 0.3 / max(step_s, 1e-6)))))
         self.barrier()
-        if K is None:  # sub-table entries: enough steps for ~5 ms of timed work, 10 ... 200
+        repeats = 1
+        if K is None:  # sub-table entries: enough steps for ~5 ms of timed work, 10 ... 200, and
+            # the MEDIAN of three such timed regions: a 1e6-event workload times ~1.5 ms per
+            # region, where one host hiccup while the launches are enqueued is a 10-25 % error
             K = int(min(200, max(10, 5e-3 / max(step_s, 1e-6))))
+            repeats = 3
 
         sampler = ClockSampler(torch.cuda.current_device()) if clocks else None
         ev0 = torch.cuda.Event(enable_timing=True)
         ev1 = torch.cuda.Event(enable_timing=True)
-        self.barrier()
-        lib.vf_launch_count(1)
-        if sampler:
-            sampler.start()
-        ev0.record()
-        events_done = self.run_steps(inst, K)
-        ev1.record()
-        self.barrier()
-        launches = int(lib.vf_launch_count(0))
-        ms = self.agree_max(ev0.elapsed_time(ev1))  # max over ranks
+        samples = []
+        for _ in range(repeats):
+            self.barrier()
+            lib.vf_launch_count(1)
+            if sampler:
+                sampler.start()
+            ev0.record()
+            events_done = self.run_steps(inst, K)
+            ev1.record()
+            self.barrier()
+            launches = int(lib.vf_launch_count(0))
+            samples.append((self.agree_max(ev0.elapsed_time(ev1)), events_done))  # max over ranks
+        ms, events_done = sorted(samples)[len(samples) // 2]
         # Second, identical K-step pass with the library's CUDA-event bracket around every
         # event-kernel / tail-kernel launch (same stream): per-kernel durations for the
         # roofline.  Kept out of the timed region because the event records break the
@@ -461,7 +468,8 @@ def main():
             t = B.measure(WORKLOADS[name], None, 3)
             table[name] = {
                 "workload": WORKLOADS[name]["name"], "value": t["value"], "unit": UNIT,
-                "steps": t["steps"], "ms_per_step": t["ms"] / t["steps"],
+                "steps": t["steps"], "timed_regions": "median of 3 regions of `steps` steps",
+                "ms_per_step": t["ms"] / t["steps"],
                 "events_per_step_per_gpu": t["per_gpu_events"],
                 "kernel_ms": t["kern_ms"], "epilogue_kernel_ms": t["epi_ms"],
                 "flops_per_event": t["f_alg"], "achieved_tflops": t["achieved"],
