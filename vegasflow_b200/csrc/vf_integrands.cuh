@@ -1,7 +1,11 @@
 // Built-in integrands, evaluated inline in the fused event kernel.
-// Every function follows the reference's operation order; the translation
-// units are compiled with -fmad=false so each multiply/add is rounded
-// separately, as TensorFlow's unfused elementwise ops are.
+// symgauss and product follow the reference's operation order bit for bit; the translation
+// units are compiled with -fmad=false so each multiply/add is rounded separately, as
+// TensorFlow's unfused elementwise ops are.  The two LO matrix elements (parity bar 1e-12 on
+// w*f, not bit-exactness) evaluate the reference's spinor chain but regroup what is exactly or
+// harmlessly equivalent -- exact-zero parts of the spinor components, square roots instead of
+// acos/sincos round trips, one collected quotient -- and keep the reference's own operations
+// wherever its rounding is amplified (see the comments at each place).
 // Reference citations are file:line relative to /root/reference.
 #pragma once
 #include "vf_common.cuh"
